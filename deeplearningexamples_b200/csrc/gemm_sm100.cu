@@ -1,0 +1,415 @@
+// Dense bf16 GEMM for sm_100a: tcgen05.mma (cta_group::1, M=128) with fp32 accumulators in TMEM,
+// operands staged by TMA into 128B-swizzled shared memory, persistent warp-specialised CTAs
+// (1 TMA producer warp, 1 MMA issuer warp, 4 epilogue warps), double-buffered accumulators so the
+// epilogue of tile i overlaps the main loop of tile i+1.
+//
+//   D[M,N] = A[M,K] * B[N,K]^T     (K = reduction)
+//
+// Either operand may be "K-major" (row-major [rows, K], the reduction dim contiguous) or
+// "MN-major" (row-major [K, rows], the M/N dim contiguous) so forward (x W^T), dgrad (dy W) and
+// wgrad (dy^T x) all read the tensors where they lie -- no transposed copies in HBM.
+//
+// This replaces the cuBLAS calls behind the reference's F.linear sites
+// (PyTorch/LanguageModeling/BERT/modeling.py:160,345-347,395,431,553) and fuses the reference's
+// separate pointwise passes (bias, tanh-GELU :121-122, dropout+residual :396-397/:432-433) into
+// the epilogue.
+#include "common.cuh"
+#include "../../include/dle_b200.h"
+
+namespace dle {
+
+constexpr int BM = 128;
+constexpr int BK = 64;        // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;
+
+template <int BN> struct GemmCfg {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int TMEM_COLS = 2 * BN;            // double-buffered accumulator
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct GemmKernelParams {
+    int M, N, K;
+    int m_tiles, n_tiles, splits, kb_total;
+    int epilogue;
+    const bf16* bias;      // [N] or null
+    const bf16* aux;       // [M, ld_aux] residual / pre-activation, or null
+    void* out;             // bf16 [M, ldo] (or fp32 for DLE_EPI_ATOMIC_F32 / DLE_EPI_F32)
+    bf16* out2;            // second output (pre-activation for DLE_EPI_BIAS_GELU)
+    long long ldo, ld_aux, ldo2;
+    float drop_scale;      // 1/(1-p)
+    uint32_t drop_thresh;  // 16-bit threshold, 0 = dropout off
+    uint32_t drop_stream;
+    unsigned long long seed;
+    float alpha;
+};
+
+// ----------------------------------------------------------------------------------------------
+// epilogue math on one 32-column strip of one row
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue_strip(const GemmKernelParams& p, const uint32_t (&acc)[32], long long row, int col0) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) * p.alpha;
+    const int ncols = min(32, p.N - col0);      // multiple of 8 (N % 8 == 0 is enforced)
+    if (ncols <= 0) return;
+
+    if (p.epilogue == DLE_EPI_ATOMIC_F32) {
+        float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + col0;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+            if (i < ncols) red_add_v4_f32(o + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+        return;
+    }
+    if (p.bias != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+            if (i < ncols) {
+                uint4 b = *reinterpret_cast<const uint4*>(p.bias + col0 + i);
+                float2 f;
+                f = unpack_bf16(b.x); v[i] += f.x; v[i + 1] += f.y;
+                f = unpack_bf16(b.y); v[i + 2] += f.x; v[i + 3] += f.y;
+                f = unpack_bf16(b.z); v[i + 4] += f.x; v[i + 5] += f.y;
+                f = unpack_bf16(b.w); v[i + 6] += f.x; v[i + 7] += f.y;
+            }
+        }
+    }
+    if (p.epilogue == DLE_EPI_F32) {
+        float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + col0;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+            if (i < ncols) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        return;
+    }
+    if (p.epilogue == DLE_EPI_BIAS_GELU) {
+        // out2 = pre-activation u (needed by gelu' in backward), out = gelu(u)
+        bf16* o2 = p.out2 + row * p.ldo2 + col0;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8)
+            if (i < ncols)
+                st_global_v4(o2 + i, pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]),
+                             pack_bf16(v[i + 4], v[i + 5]), pack_bf16(v[i + 6], v[i + 7]));
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            // gelu is evaluated on the bf16-rounded pre-activation so that backward (which only has
+            // the stored bf16 u) differentiates exactly the function forward evaluated
+            float u = __bfloat162float(__float2bfloat16_rn(v[i]));
+            v[i] = gelu_tanh(u);
+        }
+    } else if (p.epilogue == DLE_EPI_BIAS_DROPOUT_RESIDUAL) {
+        if (p.drop_thresh != 0) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+                if (i < ncols) {
+                    unsigned long long grp = (unsigned long long)(row * (long long)p.N + col0 + i) >> 3;
+                    uint32_t keep = dropout_keep8(p.seed, p.drop_stream, grp, p.drop_thresh);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[i + j] = ((keep >> j) & 1u) ? v[i + j] * p.drop_scale : 0.f;
+                }
+            }
+        }
+        if (p.aux != nullptr) {
+            const bf16* a = p.aux + row * p.ld_aux + col0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+                if (i < ncols) {
+                    uint4 b = ld_global_nc_v4(a + i);
+                    float2 f;
+                    f = unpack_bf16(b.x); v[i] += f.x; v[i + 1] += f.y;
+                    f = unpack_bf16(b.y); v[i + 2] += f.x; v[i + 3] += f.y;
+                    f = unpack_bf16(b.z); v[i + 4] += f.x; v[i + 5] += f.y;
+                    f = unpack_bf16(b.w); v[i + 6] += f.x; v[i + 7] += f.y;
+                }
+            }
+        }
+    } else if (p.epilogue == DLE_EPI_DGELU) {
+        // out = acc * gelu'(aux)   (aux = stored pre-activation u)
+        const bf16* a = p.aux + row * p.ld_aux + col0;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+            if (i < ncols) {
+                uint4 b = ld_global_nc_v4(a + i);
+                float2 f;
+                f = unpack_bf16(b.x); v[i] *= gelu_tanh_grad(f.x); v[i + 1] *= gelu_tanh_grad(f.y);
+                f = unpack_bf16(b.y); v[i + 2] *= gelu_tanh_grad(f.x); v[i + 3] *= gelu_tanh_grad(f.y);
+                f = unpack_bf16(b.z); v[i + 4] *= gelu_tanh_grad(f.x); v[i + 5] *= gelu_tanh_grad(f.y);
+                f = unpack_bf16(b.w); v[i + 6] *= gelu_tanh_grad(f.x); v[i + 7] *= gelu_tanh_grad(f.y);
+            }
+        }
+    } else if (p.epilogue == DLE_EPI_ADD) {
+        const bf16* a = p.aux + row * p.ld_aux + col0;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+            if (i < ncols) {
+                uint4 b = ld_global_nc_v4(a + i);
+                float2 f;
+                f = unpack_bf16(b.x); v[i] += f.x; v[i + 1] += f.y;
+                f = unpack_bf16(b.y); v[i + 2] += f.x; v[i + 3] += f.y;
+                f = unpack_bf16(b.z); v[i + 4] += f.x; v[i + 5] += f.y;
+                f = unpack_bf16(b.w); v[i + 6] += f.x; v[i + 7] += f.y;
+            }
+        }
+    } else if (p.epilogue == DLE_EPI_BIAS_TANH) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
+    }
+    bf16* o = reinterpret_cast<bf16*>(p.out) + row * p.ldo + col0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8)
+        if (i < ncols)
+            st_global_v4(o + i, pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]),
+                         pack_bf16(v[i + 4], v[i + 5]), pack_bf16(v[i + 6], v[i + 7]));
+}
+
+// ----------------------------------------------------------------------------------------------
+// kernel
+// ----------------------------------------------------------------------------------------------
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const GemmKernelParams p) {
+    using Cfg = GemmCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = bars;                         // [STAGES]  TMA -> MMA
+    uint64_t* empty_bar = bars + Cfg::STAGES;          // [STAGES]  MMA -> TMA
+    uint64_t* tmem_full = bars + 2 * Cfg::STAGES;      // [2]       MMA -> epilogue
+    uint64_t* tmem_empty = bars + 2 * Cfg::STAGES + 2; // [2]       epilogue -> MMA
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 128); }
+        fence_barrier_init();
+    }
+    if (warp == 2) { tmem_alloc(tmem_ptr, Cfg::TMEM_COLS); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int total_units = p.m_tiles * p.n_tiles * p.splits;
+    const int kb_per_split = (p.kb_total + p.splits - 1) / p.splits;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+                const int tile = unit / p.splits, split = unit - tile * p.splits;
+                const int m_blk = tile / p.n_tiles, n_blk = tile - m_blk * p.n_tiles;
+                const int kb0 = split * kb_per_split, kb1 = min(p.kb_total, kb0 + kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sb = sa + Cfg::A_BYTES;
+                    if (!A_MN) {
+                        tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < BM / 64; ++g)
+                            tma_load_2d(sa + g * (BK * 128), &tmap_a, &full_bar[stage], m_blk * BM + g * 64, kb * BK);
+                    }
+                    if (!B_MN) {
+                        tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < BN / 64; ++g)
+                            tma_load_2d(sb + g * (BK * 128), &tmap_b, &full_bar[stage], n_blk * BN + g * 64, kb * BK);
+                    }
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (single thread) =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+            int stage = 0; uint32_t phase = 0; int it = 0;
+            for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
+                const int split = unit % p.splits;
+                const int kb0 = split * kb_per_split, kb1 = min(p.kb_total, kb0 + kb_per_split);
+                const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // K-major:  rows of 128 B, 8-row groups 1024 B apart (SBO); advance 32 B per UMMA_K.
+                        // MN-major: k-rows of 128 B (64 m/n elements), 8-k-row groups 1024 B apart (SBO),
+                        //           next 64 m/n elements BK*128 B further (LBO); advance 16 k-rows = 2048 B.
+                        const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * (UMMA_K * 128), BK * 128, 1024)
+                                                 : make_smem_desc_sw128(sa + k * (UMMA_K * 2), 0, 1024);
+                        const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * (UMMA_K * 128), BK * 128, 1024)
+                                                 : make_smem_desc_sw128(sb + k * (UMMA_K * 2), 0, 1024);
+                        umma_bf16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);      // frees this smem stage when the MMAs retire
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);            // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue warps (TMEM -> registers -> global) =====================
+        const int q = warp & 3;                          // TMEM lane quarter owned by this warp
+        int it = 0;
+        for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
+            const int tile = unit / p.splits;
+            const int m_blk = tile / p.n_tiles, n_blk = tile - m_blk * p.n_tiles;
+            const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const long long row = (long long)m_blk * BM + q * 32 + lane;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(taddr + c * 32, r);
+                tmem_ld_wait();
+                if (row < p.M) epilogue_strip(p, r, row, n_blk * BN + c * 32);
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host
+// ----------------------------------------------------------------------------------------------
+PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn == nullptr) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+    }
+    return fn;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_cols, uint32_t box_rows) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (enc == nullptr) return DLE_ERR_CUDA;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0 || box_cols * 2 > 128 || box_rows > 256)
+        return DLE_ERR_INVALID;
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {ld * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? DLE_OK : DLE_ERR_CUDA;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const dle_gemm_args* a, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    CUtensorMap ta, tb;
+    int rc;
+    // K-major operand: matrix [rows, K] -> box {64 (k), rows_per_tile}; MN-major: matrix [K, rows] -> box {64 (m/n), 64 (k)}
+    rc = A_MN ? make_tmap_bf16_2d(&ta, a->A, a->K, a->M, a->lda, 64, BK) : make_tmap_bf16_2d(&ta, a->A, a->M, a->K, a->lda, BK, BM);
+    if (rc != DLE_OK) return rc;
+    rc = B_MN ? make_tmap_bf16_2d(&tb, a->B, a->K, a->N, a->ldb, 64, BK) : make_tmap_bf16_2d(&tb, a->B, a->N, a->K, a->ldb, BK, BN);
+    if (rc != DLE_OK) return rc;
+
+    GemmKernelParams p;
+    p.M = a->M; p.N = a->N; p.K = a->K;
+    p.m_tiles = (a->M + BM - 1) / BM;
+    p.n_tiles = (a->N + BN - 1) / BN;
+    p.kb_total = (a->K + BK - 1) / BK;
+    int splits = a->splits > 0 ? a->splits : 1;
+    if (a->epilogue != DLE_EPI_ATOMIC_F32) splits = 1;
+    if (splits > p.kb_total) splits = p.kb_total;
+    // no empty split: shrink until ceil-division leaves work for the last one
+    while (splits > 1 && (splits - 1) * ((p.kb_total + splits - 1) / splits) >= p.kb_total) --splits;
+    p.splits = splits;
+    p.epilogue = a->epilogue;
+    p.bias = reinterpret_cast<const bf16*>(a->bias);
+    p.aux = reinterpret_cast<const bf16*>(a->aux);
+    p.out = a->out;
+    p.out2 = reinterpret_cast<bf16*>(a->out2);
+    p.ldo = a->ldo; p.ld_aux = a->ld_aux; p.ldo2 = a->ldo2;
+    p.drop_thresh = (a->dropout_p > 0.f) ? dropout_thresh16(a->dropout_p) : 0u;
+    p.drop_scale = (a->dropout_p > 0.f) ? 1.0f / (1.0f - a->dropout_p) : 1.0f;
+    p.drop_stream = a->dropout_stream;
+    p.seed = a->seed;
+    p.alpha = a->alpha;
+
+    auto kern = gemm_bf16_tcgen05_kernel<BN, A_MN, B_MN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
+            return DLE_ERR_CUDA;
+        attr_set = true;
+    }
+    const int units = p.m_tiles * p.n_tiles * p.splits;
+    const int grid = units < num_sms() ? units : num_sms();
+    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+    DLE_LAUNCH_CHECK();
+    return DLE_OK;
+}
+
+}  // namespace dle
+
+extern "C" int dle_gemm_bf16(const dle_gemm_args* a, void* stream_) {
+    using namespace dle;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    DLE_CHECK_ARG(a != nullptr && a->A != nullptr && a->B != nullptr && a->out != nullptr);
+    DLE_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0);
+    DLE_CHECK_ARG(a->N % 8 == 0 && a->K % 8 == 0 && a->ldo % 8 == 0);
+    DLE_CHECK_ARG(a->epilogue >= 0 && a->epilogue < DLE_EPI_COUNT);
+    if (a->a_layout == DLE_LAYOUT_MN) DLE_CHECK_ARG(a->M % 8 == 0);
+    if (a->epilogue == DLE_EPI_BIAS_GELU) DLE_CHECK_ARG(a->out2 != nullptr && a->ldo2 % 8 == 0);
+    if (a->epilogue == DLE_EPI_DGELU || a->epilogue == DLE_EPI_ADD) DLE_CHECK_ARG(a->aux != nullptr);
+    if (a->aux != nullptr) DLE_CHECK_ARG(a->ld_aux % 8 == 0);
+    const bool amn = a->a_layout == DLE_LAYOUT_MN, bmn = a->b_layout == DLE_LAYOUT_MN;
+    // narrow-N problems (and the small-tile preference flag) take the 128-wide tile
+    const bool bn128 = (a->N <= 128) || (a->tile_n == 128);
+    if (bn128) {
+        if (!amn && !bmn) return launch_gemm<128, false, false>(a, stream);
+        if (!amn && bmn) return launch_gemm<128, false, true>(a, stream);
+        if (amn && bmn) return launch_gemm<128, true, true>(a, stream);
+        return launch_gemm<128, true, false>(a, stream);
+    }
+    if (!amn && !bmn) return launch_gemm<256, false, false>(a, stream);
+    if (!amn && bmn) return launch_gemm<256, false, true>(a, stream);
+    if (amn && bmn) return launch_gemm<256, true, true>(a, stream);
+    return launch_gemm<256, true, false>(a, stream);
+}

@@ -1,0 +1,38 @@
+"""Device-side learning-rate schedule, mirroring the reference's schedulers.PolyWarmUpScheduler
+(PyTorch/LanguageModeling/BERT/schedulers.py:109-136): every quantity is a device tensor so the
+training loop stays host-sync free and CUDA-graph capturable; `lr` is *replaced* in each param
+group by a fresh 0-dim tensor exactly as the reference does (the optimizer re-reads the pointer).
+"""
+import torch
+from torch.optim.lr_scheduler import _LRScheduler
+
+
+class PolyWarmUpScheduler(_LRScheduler):
+    def __init__(self, optimizer, warmup, total_steps, degree=0.5, last_epoch=-1, base_lr=1., device='cpu'):
+        self.warmup = torch.tensor(warmup, device=device)
+        self.total_steps = torch.tensor(total_steps, device=device)
+        self.degree = torch.tensor(degree, device=device)
+        self.base_lr = torch.tensor(base_lr, device=device)
+        self.device = device
+        # persistent lr scalar: written in place so the optimizer's device tables stay valid
+        self._lr_buf = None
+        super().__init__(optimizer, torch.tensor(last_epoch, device=device))
+
+    def step(self, epoch=None):
+        group0 = self.optimizer.param_groups[0]
+        if 'step' in group0:
+            self.last_epoch = group0['step'] + 1
+        else:
+            self.last_epoch = torch.tensor(1., device=self.device)
+        for group, lr in zip(self.optimizer.param_groups, self.get_lr()):
+            cur = group.get('lr')
+            if isinstance(cur, torch.Tensor) and cur.is_cuda and cur.dtype == torch.float32 and cur.dim() == 0:
+                cur.copy_(lr.reshape(()))          # same storage => same pointer in the LAMB plan
+            else:
+                group['lr'] = lr
+
+    def get_lr(self):
+        progress = self.last_epoch / self.total_steps
+        lr = torch.where(progress < self.warmup, self.base_lr * progress / self.warmup,
+                         self.base_lr * ((1.0 - progress) ** self.degree))
+        return [lr for _ in self.optimizer.param_groups]

@@ -2,6 +2,9 @@ import os
 import sys
 
 import pytest
+import torch
+import torch.optim  # noqa: F401  (cold import of torch._dynamo/triton can take >1 min on a fresh box: do it at collection)
+import torch.amp  # noqa: F401
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
