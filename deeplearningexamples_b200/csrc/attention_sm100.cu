@@ -1,5 +1,576 @@
-// placeholder: replaced by the tcgen05 fused attention kernels
+// Fused multi-head self-attention for sm_100a (head dim 64, S in {128,256,384,512}).
+//
+// Forward : one CTA per (batch, head, 128-query tile).  TMA stages Q, K, V of the head from the packed
+//           [T, 3H] QKV matrix into 128B-swizzled smem; tcgen05.mma computes S = Q K^T (fp32 in TMEM)
+//           128 keys at a time; 8 softmax warps run an online softmax straight out of TMEM, apply
+//           dropout (Philox, regenerated in backward) and hand P (bf16, swizzled smem) back to the
+//           tensor core for O += P V (V consumed MN-major, i.e. where the QKV GEMM wrote it).
+//           The [B,A,S,S] score tensor the reference materialises 3x per layer never exists in HBM.
+// Backward: one CTA per (batch, head); loops over (kv tile, q tile) pairs, recomputes P from the saved
+//           log-sum-exp, and accumulates dV, dK (per kv tile) and dQ (all q tiles) in TMEM -- no atomics,
+//           deterministic.  The P and dS tiles are written once to smem and read by the tensor core both
+//           K-major (dQ = dS K) and MN-major (dV = P^T dO, dK = dS^T Q): same bytes, two descriptors.
+//
+// replaces BertSelfAttention.forward, PyTorch/LanguageModeling/BERT/modeling.py:349-376
+// (transpose_for_scores, bmm, /sqrt(d), +mask, softmax, dropout, bmm, transpose+contiguous) and autograd.
 #include "common.cuh"
 #include "../../include/dle_b200.h"
-extern "C" int dle_attn_fwd(const void*, const float*, void*, float*, int32_t, int32_t, int32_t, float, uint64_t, uint32_t, void*) { return DLE_ERR_NOSYS; }
-extern "C" int dle_attn_bwd(const void*, const float*, const void*, const void*, const float*, void*, float*, int32_t, int32_t, int32_t, float, uint64_t, uint32_t, void*) { return DLE_ERR_NOSYS; }
+
+namespace dle {
+
+constexpr int HD = 64;                 // head dim
+constexpr int TQ = 128;                // query tile / key chunk
+constexpr int TILE_BYTES = TQ * HD * 2;    // 16 KB : one [128 x 64] bf16 tile (128 B rows)
+constexpr int PT_BYTES = TQ * TQ * 2;      // 32 KB : one [128 x 128] bf16 tile = two 16 KB sub-tiles
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// byte offset of 8 consecutive columns (col % 8 == 0) of row r inside a [128 x 128] bf16 tile stored as two
+// K-major SWIZZLE_128B sub-tiles (cols 0-63 | 64-127), 128 B per row, 16-byte chunks XOR-swizzled by row%8
+__device__ __forceinline__ uint32_t pt_offset(int r, int col) {
+    return (uint32_t)((col >> 6) * TILE_BYTES + r * 128 + ((((col & 63) >> 3) ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// =================================================================================================
+// forward
+// =================================================================================================
+constexpr int FWD_THREADS = 320;       // warp 0: TMA + TMEM alloc, warp 1: MMA, warps 2..9: softmax
+constexpr int FWD_SOFTMAX_THREADS = 256;
+
+struct AttnFwdParams {
+    const float* mask;     // [B,S] additive or null
+    bf16* ctx;             // [T, H]
+    float* lse;            // [B,A,S]
+    int B, S, A, H;
+    float scale_log2;      // (1/sqrt(d)) * log2(e)
+    uint32_t drop_thresh; float drop_scale; uint32_t drop_stream; unsigned long long seed;
+};
+
+__host__ __device__ inline int fwd_smem_bytes(int S) {
+    return 1024 + TILE_BYTES /*Q*/ + 2 * S * 128 /*K,V*/ + 2 * PT_BYTES /*P*/ + S * 4 /*mask*/ + 4 * TQ * 4 /*row exch*/ + 256;
+}
+
+__global__ void __launch_bounds__(FWD_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int S = p.S, n_chunks = S / TQ;
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + TILE_BYTES;
+    uint8_t* sV = sK + S * 128;
+    uint8_t* sP = sV + S * 128;
+    float* sMask = reinterpret_cast<float*>(sP + 2 * PT_BYTES);
+    float* sExch = sMask + S;                       // [2 parity][2 half][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sExch + 4 * TQ);
+    uint64_t* q_full = bars;            // 1
+    uint64_t* k_full = bars + 1;        // 4
+    uint64_t* v_full = bars + 5;        // 4
+    uint64_t* s_full = bars + 9;        // 2
+    uint64_t* p_full = bars + 11;       // 2 (count 256)
+    uint64_t* pv_done = bars + 13;      // 2
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int row0 = b * S;                       // first token row of this sequence
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_qkv);
+        mbar_init(q_full, 1);
+        for (int i = 0; i < 4; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], FWD_SOFTMAX_THREADS); mbar_init(&pv_done[i], 1); }
+        fence_barrier_init();
+    }
+    if (warp == 0) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 256;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(q_full, TILE_BYTES);
+            tma_load_2d(sQ, &tmap_qkv, q_full, h * HD, row0 + qt * TQ);
+            for (int j = 0; j < n_chunks; ++j) {
+                mbar_expect_tx(&k_full[j], TILE_BYTES);
+                tma_load_2d(sK + j * TILE_BYTES, &tmap_qkv, &k_full[j], p.H + h * HD, row0 + j * TQ);
+            }
+            for (int j = 0; j < n_chunks; ++j) {
+                mbar_expect_tx(&v_full[j], TILE_BYTES);
+                tma_load_2d(sV + j * TILE_BYTES, &tmap_qkv, &v_full[j], 2 * p.H + h * HD, row0 + j * TQ);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc_bf16(TQ, TQ, false, false);
+            constexpr uint32_t idesc_pv = make_idesc_bf16(TQ, HD, false, true);
+            const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
+            mbar_wait(q_full, 0);
+            for (int j = 0; j <= n_chunks; ++j) {
+                if (j < n_chunks) {
+                    // S_j = Q K_j^T -> TMEM S[j&1]  (buffer freed by p_full[(j-2)&1], waited in iteration j-1... see below)
+                    mbar_wait(&k_full[j], 0);
+                    tc_fence_after();
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16_ss(tmem_S + (j & 1) * TQ, make_smem_desc_sw128(aQ + kk * 32, 0, 1024),
+                                     make_smem_desc_sw128(aK + j * TILE_BYTES + kk * 32, 0, 1024), idesc_s, kk > 0 ? 1u : 0u);
+                    umma_commit(&s_full[j & 1]);
+                }
+                if (j >= 1) {
+                    const int c = j - 1;               // O += P_c V_c
+                    mbar_wait(&p_full[c & 1], (c >> 1) & 1);
+                    tc_fence_after();
+                    mbar_wait(&v_full[c], 0);
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)
+                        umma_bf16_ss(tmem_O, make_smem_desc_sw128(aP + (c & 1) * PT_BYTES + (kk >> 2) * TILE_BYTES + (kk & 3) * 32, 0, 1024),
+                                     make_smem_desc_sw128(aV + c * TILE_BYTES + kk * 2048, TILE_BYTES, 1024), idesc_pv,
+                                     (c > 0 || kk > 0) ? 1u : 0u);
+                    umma_commit(&pv_done[c & 1]);
+                }
+            }
+        }
+    } else {
+        // ===================== softmax warps =====================
+        const int q4 = warp & 3, hf = (warp - 2) >> 2;
+        const int r = q4 * 32 + lane;                                  // row inside the tile
+        const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+        const int st = threadIdx.x - 64;                               // 0..255
+        for (int i = st; i < S; i += FWD_SOFTMAX_THREADS) sMask[i] = p.mask ? p.mask[(long long)b * S + i] * LOG2E : 0.f;
+        named_bar_sync(1, FWD_SOFTMAX_THREADS);
+        float m_run = -INFINITY, l_run = 0.f;
+        const unsigned long long drop_row = ((unsigned long long)(b * p.A + h) * S + (qt * TQ + r)) * (unsigned long long)S;
+        for (int j = 0; j < n_chunks; ++j) {
+            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tS = tmem_S + lane_addr + (j & 1) * TQ + hf * 64;
+            const float* mk = sMask + j * TQ + hf * 64;
+            uint32_t v[32];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int pc = 0; pc < 2; ++pc) {
+                tmem_ld32(tS + pc * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaf(__uint_as_float(v[i]), p.scale_log2, mk[pc * 32 + i]));
+            }
+            float* ex = sExch + (j & 1) * 2 * TQ;
+            ex[hf * TQ + r] = mx;
+            named_bar_sync(1, FWD_SOFTMAX_THREADS);
+            const float m_new = fmaxf(m_run, fmaxf(ex[r], ex[TQ + r]));
+            const float alpha = ex2(m_run - m_new);                    // 0 at j == 0
+            if (j >= 1) {                                              // PV_{j-1} done: O valid, P buffer (j&1) free
+                mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+                tc_fence_after();
+            }
+            float rs = 0.f;
+            const uint32_t sp = smem_u32(sP) + (j & 1) * PT_BYTES;
+#pragma unroll
+            for (int pc = 0; pc < 2; ++pc) {
+                tmem_ld32(tS + pc * 32, v);
+                tmem_ld_wait();
+                float e[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    e[i] = ex2(fmaf(__uint_as_float(v[i]), p.scale_log2, mk[pc * 32 + i]) - m_new);
+                    rs += e[i];
+                }
+                const int col = hf * 64 + pc * 32;
+                if (p.drop_thresh != 0u) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const uint32_t keep = dropout_keep8(p.seed, p.drop_stream, (drop_row + j * TQ + col + g * 8) >> 3, p.drop_thresh);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) e[g * 8 + i] = ((keep >> i) & 1u) ? e[g * 8 + i] * p.drop_scale : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    st_shared_v4(sp + pt_offset(r, col + g * 8), pack_bf16(e[g * 8], e[g * 8 + 1]), pack_bf16(e[g * 8 + 2], e[g * 8 + 3]),
+                                 pack_bf16(e[g * 8 + 4], e[g * 8 + 5]), pack_bf16(e[g * 8 + 6], e[g * 8 + 7]));
+            }
+            if (j >= 1 && __any_sync(0xffffffffu, alpha != 1.0f)) {    // rescale my 32 columns of O
+                tmem_ld32(tmem_O + lane_addr + hf * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                tmem_st32(tmem_O + lane_addr + hf * 32, v);
+                tmem_st_wait();
+            }
+            l_run = l_run * alpha + rs;
+            m_run = m_new;
+            tc_fence_before();
+            fence_proxy_async_smem();
+            mbar_arrive(&p_full[j & 1]);
+        }
+        // ---- epilogue: O / l -> ctx, lse
+        const int last = n_chunks - 1;
+        mbar_wait(&pv_done[last & 1], (last >> 1) & 1);
+        tc_fence_after();
+        float* ex = sExch + (n_chunks & 1) * 2 * TQ;
+        ex[hf * TQ + r] = l_run;
+        named_bar_sync(1, FWD_SOFTMAX_THREADS);
+        const float l_tot = ex[r] + ex[TQ + r];
+        const float inv_l = 1.0f / l_tot;
+        uint32_t v[32];
+        tmem_ld32(tmem_O + lane_addr + hf * 32, v);
+        tmem_ld_wait();
+        const long long tok = (long long)row0 + qt * TQ + r;
+        bf16* o = p.ctx + tok * p.H + h * HD + hf * 32;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8)
+            st_global_v4(o + i, pack_bf16(__uint_as_float(v[i]) * inv_l, __uint_as_float(v[i + 1]) * inv_l),
+                         pack_bf16(__uint_as_float(v[i + 2]) * inv_l, __uint_as_float(v[i + 3]) * inv_l),
+                         pack_bf16(__uint_as_float(v[i + 4]) * inv_l, __uint_as_float(v[i + 5]) * inv_l),
+                         pack_bf16(__uint_as_float(v[i + 6]) * inv_l, __uint_as_float(v[i + 7]) * inv_l));
+        if (hf == 0) p.lse[((long long)b * p.A + h) * S + qt * TQ + r] = (m_run + log2f(l_tot)) * LN2;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+
+// =================================================================================================
+// backward
+// =================================================================================================
+constexpr int BWD_THREADS = 320;       // warp 0: TMA + TMEM alloc, warp 1: MMA, warps 2..9: compute
+constexpr int BWD_COMPUTE_THREADS = 256;
+
+struct AttnBwdParams {
+    const float* mask; const float* lse; const float* delta;
+    bf16* dqkv;            // [T, 3H]
+    int B, S, A, H;
+    float scale, scale_log2;
+    uint32_t drop_thresh; float drop_scale; uint32_t drop_stream; unsigned long long seed;
+};
+
+__host__ __device__ inline int bwd_smem_bytes(int S) {
+    return 1024 + 2 * TILE_BYTES /*K,V*/ + 4 * TILE_BYTES /*Q,dO x2*/ + 2 * PT_BYTES /*P,dS*/ + S * 4 + 256;
+}
+
+// delta[b,h,s] = sum_d dO[t, h*64+d] * O[t, h*64+d]
+__global__ void attn_delta_kernel(const bf16* __restrict__ dctx, const bf16* __restrict__ ctx, float* __restrict__ delta,
+                                  int B, int S, int A) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // token * A + h
+    const long long total = (long long)B * S * A;
+    if (idx >= total) return;
+    const long long tok = idx / A; const int h = (int)(idx - tok * A);
+    const bf16* a = dctx + tok * (long long)(A * HD) + h * HD;
+    const bf16* c = ctx + tok * (long long)(A * HD) + h * HD;
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < HD; i += 8) {
+        uint4 ua = ld_global_nc_v4(a + i), uc = ld_global_nc_v4(c + i);
+        float2 x, y;
+        x = unpack_bf16(ua.x); y = unpack_bf16(uc.x); acc += x.x * y.x + x.y * y.y;
+        x = unpack_bf16(ua.y); y = unpack_bf16(uc.y); acc += x.x * y.x + x.y * y.y;
+        x = unpack_bf16(ua.z); y = unpack_bf16(uc.z); acc += x.x * y.x + x.y * y.y;
+        x = unpack_bf16(ua.w); y = unpack_bf16(uc.w); acc += x.x * y.x + x.y * y.y;
+    }
+    const int b = (int)(tok / S), s = (int)(tok - (long long)b * S);
+    delta[((long long)b * A + h) * S + s] = acc;
+}
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do, const AttnBwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int S = p.S, n = S / TQ;
+    uint8_t* sK = smem;
+    uint8_t* sV = sK + TILE_BYTES;
+    uint8_t* sQ = sV + TILE_BYTES;               // [2]
+    uint8_t* sdO = sQ + 2 * TILE_BYTES;          // [2]
+    uint8_t* sP = sdO + 2 * TILE_BYTES;
+    uint8_t* sdS = sP + PT_BYTES;
+    float* sMask = reinterpret_cast<float*>(sdS + PT_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + S);
+    uint64_t* qdo_full = bars;        // [2]
+    uint64_t* qdo_empty = bars + 2;   // [2]
+    uint64_t* kv_full = bars + 4;
+    uint64_t* kv_empty = bars + 5;
+    uint64_t* s_full = bars + 6;
+    uint64_t* p_full = bars + 7;      // count 256
+    uint64_t* dp_full = bars + 8;
+    uint64_t* ds_full = bars + 9;     // count 256
+    uint64_t* pair_done = bars + 10;
+    uint64_t* dkv_full = bars + 11;
+    uint64_t* dkv_read = bars + 12;   // count 256
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int row0 = b * S;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_qkv); tma_prefetch_desc(&tmap_do);
+        for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
+        mbar_init(kv_full, 1); mbar_init(kv_empty, 1); mbar_init(s_full, 1); mbar_init(p_full, BWD_COMPUTE_THREADS);
+        mbar_init(dp_full, 1); mbar_init(ds_full, BWD_COMPUTE_THREADS); mbar_init(pair_done, 1); mbar_init(dkv_full, 1);
+        mbar_init(dkv_read, BWD_COMPUTE_THREADS);
+        fence_barrier_init();
+    }
+    if (warp == 0) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tmem_SP = tmem_base, tmem_dV = tmem_base + 128, tmem_dK = tmem_base + 192, tmem_dQ = tmem_base + 256;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int j = 0; j < n; ++j) {
+                mbar_wait(kv_empty, (j & 1) ^ 1);
+                mbar_expect_tx(kv_full, 2 * TILE_BYTES);
+                tma_load_2d(sK, &tmap_qkv, kv_full, p.H + h * HD, row0 + j * TQ);
+                tma_load_2d(sV, &tmap_qkv, kv_full, 2 * p.H + h * HD, row0 + j * TQ);
+                for (int i = 0; i < n; ++i) {
+                    const int t = j * n + i, st = t & 1;
+                    mbar_wait(&qdo_empty[st], ((t >> 1) & 1) ^ 1);
+                    mbar_expect_tx(&qdo_full[st], 2 * TILE_BYTES);
+                    tma_load_2d(sQ + st * TILE_BYTES, &tmap_qkv, &qdo_full[st], h * HD, row0 + i * TQ);
+                    tma_load_2d(sdO + st * TILE_BYTES, &tmap_do, &qdo_full[st], h * HD, row0 + i * TQ);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t id_kk = make_idesc_bf16(TQ, TQ, false, false);     // S, dP
+            constexpr uint32_t id_mm = make_idesc_bf16(TQ, HD, true, true);       // dV, dK
+            constexpr uint32_t id_km = make_idesc_bf16(TQ, HD, false, true);      // dQ
+            const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP), adS = smem_u32(sdS);
+            for (int j = 0; j < n; ++j) {
+                mbar_wait(kv_full, j & 1);
+                if (j >= 1) mbar_wait(dkv_read, (j - 1) & 1);       // dV/dK accumulators drained
+                tc_fence_after();
+                for (int i = 0; i < n; ++i) {
+                    const int t = j * n + i, st = t & 1;
+                    const uint32_t aQ = smem_u32(sQ) + st * TILE_BYTES, adO = smem_u32(sdO) + st * TILE_BYTES;
+                    mbar_wait(&qdo_full[st], (t >> 1) & 1);
+                    tc_fence_after();
+                    // (1) S = Q_i K_j^T
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16_ss(tmem_SP, make_smem_desc_sw128(aQ + kk * 32, 0, 1024), make_smem_desc_sw128(aK + kk * 32, 0, 1024),
+                                     id_kk, kk > 0 ? 1u : 0u);
+                    umma_commit(s_full);
+                    // (2) dP = dO_i V_j^T (overwrites S once the compute warps have consumed it) ; dV_j += P~^T dO_i
+                    mbar_wait(p_full, t & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16_ss(tmem_SP, make_smem_desc_sw128(adO + kk * 32, 0, 1024), make_smem_desc_sw128(aV + kk * 32, 0, 1024),
+                                     id_kk, kk > 0 ? 1u : 0u);
+                    umma_commit(dp_full);
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)
+                        umma_bf16_ss(tmem_dV, make_smem_desc_sw128(aP + kk * 2048, TILE_BYTES, 1024),
+                                     make_smem_desc_sw128(adO + kk * 2048, TILE_BYTES, 1024), id_mm, (i > 0 || kk > 0) ? 1u : 0u);
+                    // (3) dK_j += dS^T Q_i ; dQ_i += dS K_j
+                    mbar_wait(ds_full, t & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)
+                        umma_bf16_ss(tmem_dK, make_smem_desc_sw128(adS + kk * 2048, TILE_BYTES, 1024),
+                                     make_smem_desc_sw128(aQ + kk * 2048, TILE_BYTES, 1024), id_mm, (i > 0 || kk > 0) ? 1u : 0u);
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk)
+                        umma_bf16_ss(tmem_dQ + i * HD, make_smem_desc_sw128(adS + (kk >> 2) * TILE_BYTES + (kk & 3) * 32, 0, 1024),
+                                     make_smem_desc_sw128(aK + kk * 2048, TILE_BYTES, 1024), id_km, (j > 0 || kk > 0) ? 1u : 0u);
+                    umma_commit(&qdo_empty[st]);
+                    umma_commit(pair_done);
+                }
+                umma_commit(kv_empty);
+                umma_commit(dkv_full);
+            }
+        }
+    } else {
+        // ===================== compute warps =====================
+        const int q4 = warp & 3, hf = (warp - 2) >> 2;
+        const int r = q4 * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+        const int ct = threadIdx.x - 64;
+        for (int i = ct; i < S; i += BWD_COMPUTE_THREADS) sMask[i] = p.mask ? p.mask[(long long)b * S + i] * LOG2E : 0.f;
+        named_bar_sync(1, BWD_COMPUTE_THREADS);
+        const long long bh = (long long)b * p.A + h;
+        const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS);
+        for (int j = 0; j < n; ++j) {
+            const float* mk = sMask + j * TQ + hf * 64;
+            for (int i = 0; i < n; ++i) {
+                const int t = j * n + i;
+                const float lse2 = p.lse[bh * S + i * TQ + r] * LOG2E;
+                const float dl = p.delta[bh * S + i * TQ + r];
+                const unsigned long long drop_row = (unsigned long long)(bh * S + (i * TQ + r)) * (unsigned long long)S + j * TQ + hf * 64;
+                uint32_t pk[32];                 // undropped P, packed bf16x2 (64 values)
+                uint32_t keep_lo = 0xffffffffu, keep_hi = 0xffffffffu;
+                mbar_wait(s_full, t & 1);
+                tc_fence_after();
+                if (t >= 1) { mbar_wait(pair_done, (t - 1) & 1); tc_fence_after(); }   // sP / sdS no longer read by the tensor core
+                uint32_t v[32];
+#pragma unroll
+                for (int pc = 0; pc < 2; ++pc) {
+                    tmem_ld32(tmem_SP + lane_addr + hf * 64 + pc * 32, v);
+                    tmem_ld_wait();
+                    float e[32];
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) e[k] = ex2(fmaf(__uint_as_float(v[k]), p.scale_log2, mk[pc * 32 + k]) - lse2);
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) pk[pc * 16 + k] = pack_bf16(e[2 * k], e[2 * k + 1]);
+                    if (p.drop_thresh != 0u) {
+                        uint32_t km = 0;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const uint32_t keep = dropout_keep8(p.seed, p.drop_stream, (drop_row + pc * 32 + g * 8) >> 3, p.drop_thresh);
+                            km |= keep << (g * 8);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) e[g * 8 + k] = ((keep >> k) & 1u) ? e[g * 8 + k] * p.drop_scale : 0.f;
+                        }
+                        if (pc == 0) keep_lo = km; else keep_hi = km;
+                    }
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        st_shared_v4(aP + pt_offset(r, hf * 64 + pc * 32 + g * 8), pack_bf16(e[g * 8], e[g * 8 + 1]), pack_bf16(e[g * 8 + 2], e[g * 8 + 3]),
+                                     pack_bf16(e[g * 8 + 4], e[g * 8 + 5]), pack_bf16(e[g * 8 + 6], e[g * 8 + 7]));
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                mbar_arrive(p_full);
+                // ---- dS = P * (dP~ - delta) * scale
+                mbar_wait(dp_full, t & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int pc = 0; pc < 2; ++pc) {
+                    tmem_ld32(tmem_SP + lane_addr + hf * 64 + pc * 32, v);
+                    tmem_ld_wait();
+                    const uint32_t km = pc == 0 ? keep_lo : keep_hi;
+                    float e[32];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) {
+                        const float2 pp = unpack_bf16(pk[pc * 16 + k]);
+                        float d0 = __uint_as_float(v[2 * k]), d1 = __uint_as_float(v[2 * k + 1]);
+                        d0 = ((km >> (2 * k)) & 1u) ? d0 * p.drop_scale : 0.f;
+                        d1 = ((km >> (2 * k + 1)) & 1u) ? d1 * p.drop_scale : 0.f;
+                        e[2 * k] = pp.x * (d0 - dl) * p.scale;
+                        e[2 * k + 1] = pp.y * (d1 - dl) * p.scale;
+                    }
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        st_shared_v4(adS + pt_offset(r, hf * 64 + pc * 32 + g * 8), pack_bf16(e[g * 8], e[g * 8 + 1]), pack_bf16(e[g * 8 + 2], e[g * 8 + 3]),
+                                     pack_bf16(e[g * 8 + 4], e[g * 8 + 5]), pack_bf16(e[g * 8 + 6], e[g * 8 + 7]));
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                mbar_arrive(ds_full);
+            }
+            // ---- dV_j, dK_j complete: drain my 32 columns of each to global
+            mbar_wait(dkv_full, j & 1);
+            tc_fence_after();
+            const long long tok = (long long)row0 + j * TQ + r;
+            uint32_t v[32];
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {           // 0: dK (col block 1), 1: dV (col block 2)
+                tmem_ld32((which == 0 ? tmem_dK : tmem_dV) + lane_addr + hf * 32, v);
+                tmem_ld_wait();
+                bf16* o = p.dqkv + tok * (3LL * p.H) + (which + 1) * p.H + h * HD + hf * 32;
+#pragma unroll
+                for (int k = 0; k < 32; k += 8)
+                    st_global_v4(o + k, pack_bf16(__uint_as_float(v[k]), __uint_as_float(v[k + 1])), pack_bf16(__uint_as_float(v[k + 2]), __uint_as_float(v[k + 3])),
+                                 pack_bf16(__uint_as_float(v[k + 4]), __uint_as_float(v[k + 5])), pack_bf16(__uint_as_float(v[k + 6]), __uint_as_float(v[k + 7])));
+            }
+            tc_fence_before();
+            mbar_arrive(dkv_read);
+        }
+        // ---- all pairs done (dkv_full of the last j implies every MMA retired): drain dQ
+        for (int i = 0; i < n; ++i) {
+            uint32_t v[32];
+            tmem_ld32(tmem_dQ + i * HD + lane_addr + hf * 32, v);
+            tmem_ld_wait();
+            const long long tok = (long long)row0 + i * TQ + r;
+            bf16* o = p.dqkv + tok * (3LL * p.H) + h * HD + hf * 32;
+#pragma unroll
+            for (int k = 0; k < 32; k += 8)
+                st_global_v4(o + k, pack_bf16(__uint_as_float(v[k]), __uint_as_float(v[k + 1])), pack_bf16(__uint_as_float(v[k + 2]), __uint_as_float(v[k + 3])),
+                             pack_bf16(__uint_as_float(v[k + 4]), __uint_as_float(v[k + 5])), pack_bf16(__uint_as_float(v[k + 6]), __uint_as_float(v[k + 7])));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+}  // namespace dle
+
+using namespace dle;
+
+static int attn_check(int B, int S, int A) {
+    if (B <= 0 || A <= 0 || S <= 0 || S % TQ != 0 || S > 512) return DLE_ERR_INVALID;
+    return DLE_OK;
+}
+
+extern "C" int dle_attn_fwd(const void* qkv, const float* mask, void* ctx, float* lse, int32_t B, int32_t S, int32_t A,
+                            float dropout_p, uint64_t seed, uint32_t dropout_stream, void* stream) {
+    DLE_CHECK_ARG(qkv && ctx && lse && attn_check(B, S, A) == DLE_OK && dropout_p >= 0.f && dropout_p < 1.f);
+    const int H = A * HD;
+    CUtensorMap tm;
+    int rc = make_tmap_bf16_2d(&tm, qkv, (uint64_t)B * S, 3ull * H, 3ull * H, HD, TQ);
+    if (rc != DLE_OK) return rc;
+    AttnFwdParams p;
+    p.mask = mask; p.ctx = reinterpret_cast<bf16*>(ctx); p.lse = lse; p.B = B; p.S = S; p.A = A; p.H = H;
+    p.scale_log2 = 0.125f * LOG2E;
+    p.drop_thresh = dropout_p > 0.f ? dropout_thresh16(dropout_p) : 0u;
+    p.drop_scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
+    p.drop_stream = dropout_stream; p.seed = seed;
+    const int smem = fwd_smem_bytes(S);
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
+        if (cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return DLE_ERR_CUDA;
+        attr_smem = smem;
+    }
+    attn_fwd_kernel<<<dim3(S / TQ, A, B), FWD_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tm, p);
+    DLE_LAUNCH_CHECK();
+    return DLE_OK;
+}
+
+extern "C" int dle_attn_bwd(const void* qkv, const float* mask, const void* ctx, const void* dctx, const float* lse, void* dqkv,
+                            float* delta_ws, int32_t B, int32_t S, int32_t A, float dropout_p, uint64_t seed,
+                            uint32_t dropout_stream, void* stream) {
+    DLE_CHECK_ARG(qkv && ctx && dctx && lse && dqkv && delta_ws && attn_check(B, S, A) == DLE_OK && dropout_p >= 0.f && dropout_p < 1.f);
+    const int H = A * HD;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CUtensorMap tq, td;
+    int rc = make_tmap_bf16_2d(&tq, qkv, (uint64_t)B * S, 3ull * H, 3ull * H, HD, TQ);
+    if (rc != DLE_OK) return rc;
+    rc = make_tmap_bf16_2d(&td, dctx, (uint64_t)B * S, (uint64_t)H, (uint64_t)H, HD, TQ);
+    if (rc != DLE_OK) return rc;
+    const long long total = (long long)B * S * A;
+    attn_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(dctx), reinterpret_cast<const bf16*>(ctx), delta_ws, B, S, A);
+    DLE_LAUNCH_CHECK();
+    AttnBwdParams p;
+    p.mask = mask; p.lse = lse; p.delta = delta_ws; p.dqkv = reinterpret_cast<bf16*>(dqkv);
+    p.B = B; p.S = S; p.A = A; p.H = H; p.scale = 0.125f; p.scale_log2 = 0.125f * LOG2E;
+    p.drop_thresh = dropout_p > 0.f ? dropout_thresh16(dropout_p) : 0u;
+    p.drop_scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
+    p.drop_stream = dropout_stream; p.seed = seed;
+    const int smem = bwd_smem_bytes(S);
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
+        if (cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return DLE_ERR_CUDA;
+        attr_smem = smem;
+    }
+    attn_bwd_kernel<<<dim3(A, B), BWD_THREADS, smem, st>>>(tq, td, p);
+    DLE_LAUNCH_CHECK();
+    return DLE_OK;
+}
