@@ -40,8 +40,8 @@ class LambGroup(ctypes.Structure):
 SIGNATURES = {
     "dle_version": (_i32, [ctypes.c_char_p, _i32]),
     "dle_gemm_bf16": (_i32, [ctypes.POINTER(GemmArgs), _vp]),
-    "dle_attn_fwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _u64, _u32, _vp]),
-    "dle_attn_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _u64, _u32, _vp]),
+    "dle_attn_fwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _u64, _u32, _vp]),
+    "dle_attn_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _u64, _u32, _vp]),
     "dle_add_ln_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _u64, _u32, _vp]),
     "dle_ln_bwd_partials": (_i32, [_i64]),
     "dle_add_ln_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _u64, _u32, _vp]),

@@ -53,6 +53,7 @@ struct AttnFwdParams {
     bf16* ctx;             // [T, H]
     float* lse;            // [B,A,S]
     int B, S, A, H;
+    int tok_stride_s, tok_stride_b;   // token row of (b, s) = b*tok_stride_b + s*tok_stride_s
     float scale_log2;      // (1/sqrt(d)) * log2(e)
     uint32_t drop_thresh; float drop_scale; uint32_t drop_stream; unsigned long long seed;
 };
@@ -83,7 +84,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdParam
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-    const int row0 = b * S;                       // first token row of this sequence
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_qkv);
@@ -102,14 +102,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdParam
     if (warp == 0) {
         if (lane == 0) {
             mbar_expect_tx(q_full, TILE_BYTES);
-            tma_load_2d(sQ, &tmap_qkv, q_full, h * HD, row0 + qt * TQ);
+            tma_load_3d(sQ, &tmap_qkv, q_full, h * HD, qt * TQ, b);
             for (int j = 0; j < n_chunks; ++j) {
                 mbar_expect_tx(&k_full[j], TILE_BYTES);
-                tma_load_2d(sK + j * TILE_BYTES, &tmap_qkv, &k_full[j], p.H + h * HD, row0 + j * TQ);
+                tma_load_3d(sK + j * TILE_BYTES, &tmap_qkv, &k_full[j], p.H + h * HD, j * TQ, b);
             }
             for (int j = 0; j < n_chunks; ++j) {
                 mbar_expect_tx(&v_full[j], TILE_BYTES);
-                tma_load_2d(sV + j * TILE_BYTES, &tmap_qkv, &v_full[j], 2 * p.H + h * HD, row0 + j * TQ);
+                tma_load_3d(sV + j * TILE_BYTES, &tmap_qkv, &v_full[j], 2 * p.H + h * HD, j * TQ, b);
             }
         }
     } else if (warp == 1) {
@@ -228,7 +228,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdParam
         uint32_t v[32];
         tmem_ld32(tmem_O + lane_addr + hf * 32, v);
         tmem_ld_wait();
-        const long long tok = (long long)row0 + qt * TQ + r;
+        const long long tok = (long long)b * p.tok_stride_b + (long long)(qt * TQ + r) * p.tok_stride_s;
         bf16* o = p.ctx + tok * p.H + h * HD + hf * 32;
 #pragma unroll
         for (int i = 0; i < 32; i += 8)
@@ -254,6 +254,7 @@ struct AttnBwdParams {
     const float* mask; const float* lse; const float* delta;
     bf16* dqkv;            // [T, 3H]
     int B, S, A, H;
+    int tok_stride_s, tok_stride_b;
     float scale, scale_log2;
     uint32_t drop_thresh; float drop_scale; uint32_t drop_stream; unsigned long long seed;
 };
@@ -264,7 +265,7 @@ __host__ __device__ inline int bwd_smem_bytes(int S) {
 
 // delta[b,h,s] = sum_d dO[t, h*64+d] * O[t, h*64+d]
 __global__ void attn_delta_kernel(const bf16* __restrict__ dctx, const bf16* __restrict__ ctx, float* __restrict__ delta,
-                                  int B, int S, int A) {
+                                  int B, int S, int A, int seq_first) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // token * A + h
     const long long total = (long long)B * S * A;
     if (idx >= total) return;
@@ -281,7 +282,8 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ dctx, const bf16* __r
         x = unpack_bf16(ua.z); y = unpack_bf16(uc.z); acc += x.x * y.x + x.y * y.y;
         x = unpack_bf16(ua.w); y = unpack_bf16(uc.w); acc += x.x * y.x + x.y * y.y;
     }
-    const int b = (int)(tok / S), s = (int)(tok - (long long)b * S);
+    const int b = seq_first ? (int)(tok % B) : (int)(tok / S);
+    const int s = seq_first ? (int)(tok / B) : (int)(tok - (long long)b * S);
     delta[((long long)b * A + h) * S + s] = acc;
 }
 
@@ -313,7 +315,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = blockIdx.x, b = blockIdx.y;
-    const int row0 = b * S;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_qkv); tma_prefetch_desc(&tmap_do);
@@ -335,14 +336,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             for (int j = 0; j < n; ++j) {
                 mbar_wait(kv_empty, (j & 1) ^ 1);
                 mbar_expect_tx(kv_full, 2 * TILE_BYTES);
-                tma_load_2d(sK, &tmap_qkv, kv_full, p.H + h * HD, row0 + j * TQ);
-                tma_load_2d(sV, &tmap_qkv, kv_full, 2 * p.H + h * HD, row0 + j * TQ);
+                tma_load_3d(sK, &tmap_qkv, kv_full, p.H + h * HD, j * TQ, b);
+                tma_load_3d(sV, &tmap_qkv, kv_full, 2 * p.H + h * HD, j * TQ, b);
                 for (int i = 0; i < n; ++i) {
                     const int t = j * n + i, st = t & 1;
                     mbar_wait(&qdo_empty[st], ((t >> 1) & 1) ^ 1);
                     mbar_expect_tx(&qdo_full[st], 2 * TILE_BYTES);
-                    tma_load_2d(sQ + st * TILE_BYTES, &tmap_qkv, &qdo_full[st], h * HD, row0 + i * TQ);
-                    tma_load_2d(sdO + st * TILE_BYTES, &tmap_do, &qdo_full[st], h * HD, row0 + i * TQ);
+                    tma_load_3d(sQ + st * TILE_BYTES, &tmap_qkv, &qdo_full[st], h * HD, i * TQ, b);
+                    tma_load_3d(sdO + st * TILE_BYTES, &tmap_do, &qdo_full[st], h * HD, i * TQ, b);
                 }
             }
         }
@@ -478,7 +479,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             // ---- dV_j, dK_j complete: drain my 32 columns of each to global
             mbar_wait(dkv_full, j & 1);
             tc_fence_after();
-            const long long tok = (long long)row0 + j * TQ + r;
+            const long long tok = (long long)b * p.tok_stride_b + (long long)(j * TQ + r) * p.tok_stride_s;
             uint32_t v[32];
 #pragma unroll
             for (int which = 0; which < 2; ++which) {           // 0: dK (col block 1), 1: dV (col block 2)
@@ -498,7 +499,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             uint32_t v[32];
             tmem_ld32(tmem_dQ + i * HD + lane_addr + hf * 32, v);
             tmem_ld_wait();
-            const long long tok = (long long)row0 + i * TQ + r;
+            const long long tok = (long long)b * p.tok_stride_b + (long long)(i * TQ + r) * p.tok_stride_s;
             bf16* o = p.dqkv + tok * (3LL * p.H) + h * HD + hf * 32;
 #pragma unroll
             for (int k = 0; k < 32; k += 8)
@@ -515,19 +516,37 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
 
 using namespace dle;
 
+// 3-D view {cols, S, B} of a [tokens, cols] bf16 matrix whose token rows are ordered b*S+s (seq_first=0)
+// or s*B+b (seq_first=1, the reference's [S,B,H] convention); box = {64 cols, 128 s, 1 b}
+static int make_tmap_tokens_3d(CUtensorMap* out, const void* base, int B, int S, int cols, int seq_first) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (enc == nullptr) return DLE_ERR_CUDA;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (cols * 2) % 16 != 0) return DLE_ERR_INVALID;
+    const cuuint64_t row_bytes = (cuuint64_t)cols * 2;
+    cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)S, (cuuint64_t)B};
+    cuuint64_t gstride[2] = {seq_first ? row_bytes * B : row_bytes, seq_first ? row_bytes : row_bytes * S};
+    cuuint32_t box[3] = {HD, TQ, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? DLE_OK : DLE_ERR_CUDA;
+}
+
 static int attn_check(int B, int S, int A) {
     if (B <= 0 || A <= 0 || S <= 0 || S % TQ != 0 || S > 512) return DLE_ERR_INVALID;
     return DLE_OK;
 }
 
 extern "C" int dle_attn_fwd(const void* qkv, const float* mask, void* ctx, float* lse, int32_t B, int32_t S, int32_t A,
-                            float dropout_p, uint64_t seed, uint32_t dropout_stream, void* stream) {
+                            int32_t seq_first, float dropout_p, uint64_t seed, uint32_t dropout_stream, void* stream) {
     DLE_CHECK_ARG(qkv && ctx && lse && attn_check(B, S, A) == DLE_OK && dropout_p >= 0.f && dropout_p < 1.f);
     const int H = A * HD;
     CUtensorMap tm;
-    int rc = make_tmap_bf16_2d(&tm, qkv, (uint64_t)B * S, 3ull * H, 3ull * H, HD, TQ);
+    int rc = make_tmap_tokens_3d(&tm, qkv, B, S, 3 * H, seq_first);
     if (rc != DLE_OK) return rc;
     AttnFwdParams p;
+    p.tok_stride_s = seq_first ? B : 1; p.tok_stride_b = seq_first ? 1 : S;
     p.mask = mask; p.ctx = reinterpret_cast<bf16*>(ctx); p.lse = lse; p.B = B; p.S = S; p.A = A; p.H = H;
     p.scale_log2 = 0.125f * LOG2E;
     p.drop_thresh = dropout_p > 0.f ? dropout_thresh16(dropout_p) : 0u;
@@ -545,22 +564,22 @@ extern "C" int dle_attn_fwd(const void* qkv, const float* mask, void* ctx, float
 }
 
 extern "C" int dle_attn_bwd(const void* qkv, const float* mask, const void* ctx, const void* dctx, const float* lse, void* dqkv,
-                            float* delta_ws, int32_t B, int32_t S, int32_t A, float dropout_p, uint64_t seed,
+                            float* delta_ws, int32_t B, int32_t S, int32_t A, int32_t seq_first, float dropout_p, uint64_t seed,
                             uint32_t dropout_stream, void* stream) {
     DLE_CHECK_ARG(qkv && ctx && dctx && lse && dqkv && delta_ws && attn_check(B, S, A) == DLE_OK && dropout_p >= 0.f && dropout_p < 1.f);
     const int H = A * HD;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     CUtensorMap tq, td;
-    int rc = make_tmap_bf16_2d(&tq, qkv, (uint64_t)B * S, 3ull * H, 3ull * H, HD, TQ);
+    int rc = make_tmap_tokens_3d(&tq, qkv, B, S, 3 * H, seq_first);
     if (rc != DLE_OK) return rc;
-    rc = make_tmap_bf16_2d(&td, dctx, (uint64_t)B * S, (uint64_t)H, (uint64_t)H, HD, TQ);
+    rc = make_tmap_tokens_3d(&td, dctx, B, S, H, seq_first);
     if (rc != DLE_OK) return rc;
     const long long total = (long long)B * S * A;
-    attn_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(dctx), reinterpret_cast<const bf16*>(ctx), delta_ws, B, S, A);
+    attn_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(dctx), reinterpret_cast<const bf16*>(ctx), delta_ws, B, S, A, seq_first);
     DLE_LAUNCH_CHECK();
     AttnBwdParams p;
     p.mask = mask; p.lse = lse; p.delta = delta_ws; p.dqkv = reinterpret_cast<bf16*>(dqkv);
-    p.B = B; p.S = S; p.A = A; p.H = H; p.scale = 0.125f; p.scale_log2 = 0.125f * LOG2E;
+    p.B = B; p.S = S; p.A = A; p.H = H; p.tok_stride_s = seq_first ? B : 1; p.tok_stride_b = seq_first ? 1 : S; p.scale = 0.125f; p.scale_log2 = 0.125f * LOG2E;
     p.drop_thresh = dropout_p > 0.f ? dropout_thresh16(dropout_p) : 0u;
     p.drop_scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
     p.drop_stream = dropout_stream; p.seed = seed;

@@ -78,24 +78,24 @@ def gemm(a, b, *, a_layout=L.LAYOUT_K, b_layout=L.LAYOUT_K, epilogue=L.EPI_BIAS,
 # ------------------------------------------------------------------------------------------------
 # attention
 # ------------------------------------------------------------------------------------------------
-def attn_fwd(qkv, mask, B, S, A, dropout_p=0.0, seed=0, dropout_stream=0):
+def attn_fwd(qkv, mask, B, S, A, dropout_p=0.0, seed=0, dropout_stream=0, seq_first=False):
     lib = L.load()
     _req(qkv, bf16, "qkv")
     ctx = torch.empty((B * S, A * 64), device=qkv.device, dtype=bf16)
     lse = torch.empty((B, A, S), device=qkv.device, dtype=torch.float32)
     if mask is not None:
         _req(mask, torch.float32, "mask")
-    L.check(lib.dle_attn_fwd(_ptr(qkv), _ptr(mask), _ptr(ctx), _ptr(lse), B, S, A, dropout_p, seed, dropout_stream,
-                             _stream()), "dle_attn_fwd")
+    L.check(lib.dle_attn_fwd(_ptr(qkv), _ptr(mask), _ptr(ctx), _ptr(lse), B, S, A, 1 if seq_first else 0, dropout_p, seed,
+                             dropout_stream, _stream()), "dle_attn_fwd")
     return ctx, lse
 
 
-def attn_bwd(qkv, mask, ctx, dctx, lse, B, S, A, dropout_p=0.0, seed=0, dropout_stream=0):
+def attn_bwd(qkv, mask, ctx, dctx, lse, B, S, A, dropout_p=0.0, seed=0, dropout_stream=0, seq_first=False):
     lib = L.load()
     dqkv = torch.empty_like(qkv)
     delta = torch.empty((B, A, S), device=qkv.device, dtype=torch.float32)
     L.check(lib.dle_attn_bwd(_ptr(qkv), _ptr(mask), _ptr(ctx), _ptr(_req(dctx, bf16, "dctx")), _ptr(lse), _ptr(dqkv),
-                             _ptr(delta), B, S, A, dropout_p, seed, dropout_stream, _stream()), "dle_attn_bwd")
+                             _ptr(delta), B, S, A, 1 if seq_first else 0, dropout_p, seed, dropout_stream, _stream()), "dle_attn_bwd")
     return dqkv
 
 

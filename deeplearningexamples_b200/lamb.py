@@ -53,6 +53,7 @@ class FusedLAMBAMP(torch.optim.Optimizer):
         self._global_grad_norm = torch.zeros(1, dtype=torch.float32, device=device)
         self._plan = None
         self._plan_sig = None
+        self._lr_dev = []
 
     def __del__(self):
         self._drop_plan()
@@ -140,12 +141,18 @@ class FusedLAMBAMP(torch.optim.Optimizer):
         for gi, (group, g32) in enumerate(zip(self.param_groups, self.param_groups_fp32)):
             beta1, beta2 = group['betas']
             lg = L.LambGroup()
-            lg.lr, lg.step = group['lr'].data_ptr(), group['step'].data_ptr()
+            # the kernels read lr from a buffer owned by this optimizer: schedulers may REPLACE group['lr'] by a new
+            # tensor every step (reference schedulers.py:129-130), which must not invalidate the device tables
+            while len(self._lr_dev) <= gi:
+                self._lr_dev.append(torch.zeros((), dtype=torch.float32, device=group['params'][0].device))
+            if not isinstance(group['step'], torch.Tensor):
+                group['step'] = torch.tensor([int(group['step'])], dtype=torch.int, device=group['params'][0].device)
+            lg.lr, lg.step = self._lr_dev[gi].data_ptr(), group['step'].data_ptr()
             lg.beta1, lg.beta2, lg.eps, lg.weight_decay = beta1, beta2, group['eps'], group['weight_decay']
             lg.bias_correction = 1 if group['bias_correction'] else 0
             lg.grad_averaging = 1 if group['grad_averaging'] else 0
             groups.append(lg)
-            sig.append((group['lr'].data_ptr(), group['step'].data_ptr(), beta1, beta2, group['eps'], group['weight_decay']))
+            sig.append((group['step'].data_ptr(), beta1, beta2, group['eps'], group['weight_decay']))
             for p, p32 in zip(group['params'], g32['params']):
                 if p.grad is None:
                     continue
@@ -177,8 +184,12 @@ class FusedLAMBAMP(torch.optim.Optimizer):
         return (tensors, groups, L.DLE_DTYPE_BF16 if torch.bfloat16 in grad_dtypes else L.DLE_DTYPE_F32), tuple(sig)
 
     def _grad_signature(self):
-        return tuple(p.grad.data_ptr() if p.grad is not None else 0
-                     for g in self.param_groups for p in g['params'])
+        sig = [g['step'].data_ptr() if isinstance(g['step'], torch.Tensor) else -1 for g in self.param_groups]
+        for g in self.param_groups:
+            for p in g['params']:
+                sig.append(p.data_ptr())
+                sig.append(p.grad.data_ptr() if p.grad is not None else 0)
+        return tuple(sig)
 
     def _ensure_plan(self):
         gsig = self._grad_signature()
@@ -207,6 +218,12 @@ class FusedLAMBAMP(torch.optim.Optimizer):
         if self._plan is None:
             return loss
         device = self.param_groups[0]["params"][0].device
+        for gi, group in enumerate(self.param_groups):
+            lr = group['lr']
+            if isinstance(lr, torch.Tensor):
+                self._lr_dev[gi].copy_(lr.reshape(()), non_blocking=True)
+            else:
+                self._lr_dev[gi].fill_(float(lr))
         scale = None
         if grad_scaler is not None and grad_scaler.is_enabled():
             scale = grad_scaler._get_scale_async()
@@ -216,6 +233,8 @@ class FusedLAMBAMP(torch.optim.Optimizer):
                                        1 if self.use_nvlamb else 0, ctypes.c_void_p(self._found_inf.data_ptr()),
                                        ctypes.c_void_p(self._global_grad_norm.data_ptr()), ctypes.c_void_p(0), stream),
                 "dle_lamb_step")
+        from . import ops
+        ops.weight_epoch["n"] += 1          # parameters changed through raw pointers: invalidate cached bf16 copies
         if grad_scaler is not None and grad_scaler.is_enabled():
             # what GradScaler._check_inf_per_device would have recorded (fused_lamb.py:148-151)
             grad_scaler._per_optimizer_states[id(self)]["found_inf_per_device"] = {device: self._found_inf}

@@ -1,0 +1,251 @@
+"""Autograd functions composing the sm_100a kernels into the operations the reference's modules perform.
+
+Each Function is hand-differentiated: forward and backward call the C ABI (kernels.py) only; torch is
+used for memory, streams and the autograd graph.  Activations are bf16 [tokens, features].
+
+Saved-for-backward policy (per encoder layer, T = B*S tokens): qkv [T,3H], ctx [T,H], lse; z1 (pre-LN
+sum), mean/rstd; u (pre-GELU) and g = gelu(u) [T,I]; z2.  Dropout masks are never stored: they are
+regenerated from (seed, stream id) by the same counter-based RNG in forward and backward.
+"""
+import torch
+
+from . import _lib as L
+from . import kernels as K
+
+bf16 = torch.bfloat16
+
+# -------------------------------------------------------------------------------------------------
+# RNG bookkeeping for dropout: one 64-bit seed per forward call site, drawn from a host counter.
+# -------------------------------------------------------------------------------------------------
+_rng = {"base": None, "counter": 0}
+_MASK64 = (1 << 64) - 1
+
+
+def manual_seed(seed):
+    _rng["base"] = int(seed) & _MASK64
+    _rng["counter"] = 0
+
+
+def next_seed():
+    if _rng["base"] is None:
+        _rng["base"] = torch.initial_seed() & _MASK64
+    _rng["counter"] += 1
+    return (_rng["base"] * 0x9E3779B97F4A7C15 + _rng["counter"] * 0xD1B54A32D192ED03) & _MASK64
+
+
+_stream_ids = {"next": 1}
+
+
+def new_stream_id():
+    """Distinct RNG stream per dropout call site (module instance)."""
+    _stream_ids["next"] += 1
+    return _stream_ids["next"]
+
+
+# -------------------------------------------------------------------------------------------------
+# bf16 views of parameters (fp32-parameter / autocast-style use keeps a cached bf16 copy)
+# -------------------------------------------------------------------------------------------------
+_w16_cache = {}
+weight_epoch = {"n": 0}          # bumped by FusedLAMBAMP.step (in-place updates through raw pointers)
+
+
+def w16(p, key=None):
+    """bf16 tensor holding parameter p's values (p itself when it already is bf16).  `key`: the parameter whose
+    version counter governs the cache when p is a derived view (packed q|k|v block)."""
+    if p is None:
+        return None
+    t = p.detach()
+    if t.dtype == bf16:
+        return t
+    if t.dtype != torch.float32:
+        raise L.DleError(f"parameters must be bf16 or fp32, got {t.dtype}")
+    owner = p if key is None else key
+    key = (id(owner), tuple(t.shape))
+    ent = _w16_cache.get(key)
+    sig = (t.data_ptr(), owner._version, weight_epoch["n"])
+    if ent is None or ent[0] != sig:
+        buf = ent[1] if (ent is not None and ent[1].shape == t.shape) else torch.empty(t.shape, device=t.device, dtype=bf16)
+        K.cast_f32_to_bf16(t.contiguous(), buf)
+        ent = (sig, buf)
+        _w16_cache[key] = ent
+    return ent[1]
+
+
+def _to_param_dtype(g, p):
+    return g if g.dtype == p.dtype else g.to(p.dtype)
+
+
+def _sm_count():
+    return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+
+
+def wgrad(dy, x, out_dtype):
+    """dW[N_out, K_in] = dy[T, N_out]^T @ x[T, K_in]; both operands read MN-major where they lie.
+    Few output tiles => split-K over tokens with fp32 red.global.add; otherwise direct store."""
+    T, n_out = dy.shape
+    k_in = x.shape[1]
+    tiles = ((n_out + 127) // 128) * ((k_in + 255) // 256)
+    sms = _sm_count()
+    if tiles >= sms * 3 // 4:
+        if out_dtype == torch.float32:
+            return K.gemm(dy, x, a_layout=L.LAYOUT_MN, b_layout=L.LAYOUT_MN, epilogue=L.EPI_F32)
+        return K.gemm(dy, x, a_layout=L.LAYOUT_MN, b_layout=L.LAYOUT_MN, epilogue=L.EPI_BIAS)
+    splits = max(1, min((sms + tiles - 1) // tiles, (T + 511) // 512))
+    acc = K.gemm(dy, x, a_layout=L.LAYOUT_MN, b_layout=L.LAYOUT_MN, epilogue=L.EPI_ATOMIC_F32, splits=splits)
+    return acc if out_dtype == torch.float32 else K.cast_f32_to_bf16(acc)
+
+
+def _bias_grad(dy, p):
+    return None if p is None else _to_param_dtype(K.colsum(dy), p)
+
+
+# -------------------------------------------------------------------------------------------------
+# y = act(x W^T + b)          act in {none, gelu_tanh, tanh}
+# replaces nn.Linear / LinearActivation (modeling.py:130-160)
+# -------------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, act):
+        w, b = w16(weight), w16(bias)
+        ctx.act = act
+        if act == "gelu":
+            y, u = K.gemm(x, w, bias=b, epilogue=L.EPI_BIAS_GELU)
+            ctx.save_for_backward(x, weight, bias, u)
+        elif act == "tanh":
+            y = K.gemm(x, w, bias=b, epilogue=L.EPI_BIAS_TANH)
+            ctx.save_for_backward(x, weight, bias, y)
+        else:
+            y = K.gemm(x, w, bias=b, epilogue=L.EPI_BIAS)
+            ctx.save_for_backward(x, weight, bias, None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, bias, aux = ctx.saved_tensors
+        dy = dy.contiguous()
+        if ctx.act == "gelu":
+            dy = K.bias_gelu_bwd(dy, aux)
+        elif ctx.act == "tanh":
+            dy = (dy.float() * (1.0 - aux.float() ** 2)).to(bf16)      # [B,H] pooler only
+        dx = K.gemm(dy, w16(weight), b_layout=L.LAYOUT_MN) if ctx.needs_input_grad[0] else None
+        dw = wgrad(dy, x, weight.dtype) if ctx.needs_input_grad[1] else None
+        db = _bias_grad(dy, bias) if (bias is not None and ctx.needs_input_grad[2]) else None
+        return dx, dw, db, None
+
+
+# -------------------------------------------------------------------------------------------------
+# y = LayerNorm(dropout(x W^T + b) + residual)
+# replaces BertSelfOutput.forward / BertOutput.forward (modeling.py:394-398, 430-434)
+# -------------------------------------------------------------------------------------------------
+class DenseDropoutAddLNFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, residual, weight, bias, gamma, beta, p_drop, eps, stream_id):
+        seed = next_seed() if p_drop > 0.0 else 0
+        z = K.gemm(x, w16(weight), bias=w16(bias), aux=residual, epilogue=L.EPI_BIAS_DROPOUT_RESIDUAL,
+                   dropout_p=p_drop, seed=seed, dropout_stream=stream_id)
+        y, _, mean, rstd = K.add_ln_fwd(z, w16(gamma), w16(beta), eps=eps)
+        ctx.save_for_backward(x, weight, bias, gamma, beta, z, mean, rstd)
+        ctx.p_drop, ctx.seed, ctx.stream_id = p_drop, seed, stream_id
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, bias, gamma, beta, z, mean, rstd = ctx.saved_tensors
+        dz, dh, dgamma, dbeta, dbias = K.add_ln_bwd(dy.contiguous(), z, mean, rstd, w16(gamma), dropout_p=ctx.p_drop,
+                                                    seed=ctx.seed, dropout_stream=ctx.stream_id)
+        dx = K.gemm(dh, w16(weight), b_layout=L.LAYOUT_MN)
+        dw = wgrad(dh, x, weight.dtype)
+        return (dx, dz, dw, _to_param_dtype(dbias, bias), _to_param_dtype(dgamma, gamma), _to_param_dtype(dbeta, beta),
+                None, None, None)
+
+
+# -------------------------------------------------------------------------------------------------
+# packed QKV projection + fused attention
+# replaces BertSelfAttention.forward (modeling.py:340-384)
+# -------------------------------------------------------------------------------------------------
+class SelfAttentionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, wq, wk, wv, bq, bk, bv, w_packed, b_packed, mask, B, S, A, p_drop, stream_id, seq_first):
+        """x [T,H]; wq/wk/wv, bq/bk/bv: the three nn.Linear parameters (autograd leaves) whose storage is one
+        packed block; w_packed [3H,H] / b_packed [3H]: views over that block; mask fp32 [B,S] additive or None."""
+        seed = next_seed() if p_drop > 0.0 else 0
+        w, b = w16(w_packed, key=wq), w16(b_packed, key=bq)
+        qkv = K.gemm(x, w, bias=b)
+        out, lse = K.attn_fwd(qkv, mask, B, S, A, dropout_p=p_drop, seed=seed, dropout_stream=stream_id, seq_first=seq_first)
+        ctx.save_for_backward(x, w_packed, mask, qkv, out, lse)
+        ctx.cfg = (B, S, A, p_drop, seed, stream_id, seq_first)
+        ctx.params = (wq, bq)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w_packed, mask, qkv, out, lse = ctx.saved_tensors
+        B, S, A, p_drop, seed, stream_id, seq_first = ctx.cfg
+        wq, bq = ctx.params
+        dqkv = K.attn_bwd(qkv, mask, out, dout.contiguous(), lse, B, S, A, dropout_p=p_drop, seed=seed,
+                          dropout_stream=stream_id, seq_first=seq_first)
+        dx = K.gemm(dqkv, w16(w_packed, key=wq), b_layout=L.LAYOUT_MN)
+        dw = wgrad(dqkv, x, wq.dtype)                       # [3H, H]
+        db = _to_param_dtype(K.colsum(dqkv), bq)            # [3H]
+        H = dw.shape[1]
+        return (dx, dw[0:H], dw[H:2 * H], dw[2 * H:3 * H], db[0:H], db[H:2 * H], db[2 * H:3 * H],
+                None, None, None, None, None, None, None, None, None)
+
+
+# -------------------------------------------------------------------------------------------------
+# embeddings: dropout(LayerNorm(word[ids] + pos[arange(S)] + type[tt]))
+# replaces BertEmbeddings.forward (modeling.py:285-301)
+# -------------------------------------------------------------------------------------------------
+class EmbeddingLNFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, input_ids, token_type_ids, word, pos, typ, gamma, beta, p_drop, eps, stream_id):
+        seed = next_seed() if p_drop > 0.0 else 0
+        ids, tts = input_ids.contiguous(), token_type_ids.contiguous()
+        err = torch.zeros(1, dtype=torch.int32, device=word.device)
+        y, z, mean, rstd = K.embed_ln_fwd(ids, tts, w16(word), w16(pos), w16(typ), w16(gamma), w16(beta), eps=eps,
+                                          dropout_p=p_drop, seed=seed, dropout_stream=stream_id, err_flag=err)
+        ctx.save_for_backward(ids, tts, word, pos, typ, gamma, beta, z, mean, rstd)
+        ctx.cfg = (p_drop, seed, stream_id)
+        ctx.err_flag = err              # checked lazily (no host sync in the hot loop)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        ids, tts, word, pos, typ, gamma, beta, z, mean, rstd = ctx.saved_tensors
+        p_drop, seed, stream_id = ctx.cfg
+        dword, dpos, dtyp, dgamma, dbeta = K.embed_ln_bwd(dy.contiguous(), z, mean, rstd, w16(gamma), ids, tts,
+                                                          word.shape[0], pos.shape[0], typ.shape[0], dropout_p=p_drop,
+                                                          seed=seed, dropout_stream=stream_id)
+        cast = lambda g, p: g if p.dtype == torch.float32 else K.cast_f32_to_bf16(g)
+        return (None, None, cast(dword, word), cast(dpos, pos), cast(dtyp, typ), _to_param_dtype(dgamma, gamma),
+                _to_param_dtype(dbeta, beta), None, None, None)
+
+
+# -------------------------------------------------------------------------------------------------
+# plain LayerNorm (MLM transform, modeling.py:534) and masked-row gather (modeling.py:590)
+# -------------------------------------------------------------------------------------------------
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        y, _, mean, rstd = K.add_ln_fwd(x, w16(gamma), w16(beta), eps=eps)
+        ctx.save_for_backward(x, gamma, beta, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta, mean, rstd = ctx.saved_tensors
+        dz, _, dgamma, dbeta = K.add_ln_bwd(dy.contiguous(), x, mean, rstd, w16(gamma), want_dbias=False)
+        return dz, _to_param_dtype(dgamma, gamma), _to_param_dtype(dbeta, beta), None
+
+
+class GatherRowsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, idx):
+        ctx.save_for_backward(idx)
+        ctx.n_rows = x.shape[0]
+        return K.gather_rows(x, idx)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        return K.scatter_rows(dy.contiguous(), idx, ctx.n_rows), None

@@ -89,13 +89,15 @@ int dle_gemm_bf16(const dle_gemm_args* host_args, void* stream);
  *   of one QKV projection GEMM.   mask: fp32 additive [B, S] ((1-m)*-10000, modeling.py:864-872)
  *   or NULL.   ctx/dctx: bf16 [B*S, A*64].   lse: fp32 [B, A, S] (natural-log sum-exp of the
  *   scaled+masked scores, saved for backward).   head dim is fixed at 64; S % 128 == 0, S <= 512.
+ * seq_first: 0 = token rows ordered b*S+s ([B,S,*]); 1 = s*B+b (the reference's [S,B,*] layer convention,
+ *   modeling.py:330-338,498) -- both are read in place through 3-D TMA maps.
  * ------------------------------------------------------------------------------------------ */
 int dle_attn_fwd(const void* qkv, const float* mask, void* ctx, float* lse, int32_t B, int32_t S, int32_t A,
-                 float dropout_p, uint64_t seed, uint32_t dropout_stream, void* stream);
+                 int32_t seq_first, float dropout_p, uint64_t seed, uint32_t dropout_stream, void* stream);
 /* delta_ws: fp32 workspace [B, A, S]; dqkv: bf16 [B*S, 3*A*64], fully overwritten */
 int dle_attn_bwd(const void* qkv, const float* mask, const void* ctx, const void* dctx, const float* lse,
-                 void* dqkv, float* delta_ws, int32_t B, int32_t S, int32_t A, float dropout_p, uint64_t seed,
-                 uint32_t dropout_stream, void* stream);
+                 void* dqkv, float* delta_ws, int32_t B, int32_t S, int32_t A, int32_t seq_first, float dropout_p,
+                 uint64_t seed, uint32_t dropout_stream, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (bias +) dropout + residual-add + LayerNorm, vectorised warp-shuffle kernels (HBM-bound)

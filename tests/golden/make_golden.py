@@ -78,6 +78,12 @@ def run(modeling, cfg, sd, batch, capture_layers):
     return dict(scores=scores.detach(), nsp=nsp.detach(), loss=loss.detach(), acts=acts, grads=grads)
 
 
+SMALL_GRAD_KEYS = ["bert.encoder.layer.0.attention.self.query.weight", "bert.encoder.layer.0.attention.self.value.bias",
+                   "bert.encoder.layer.1.intermediate.dense_act.weight", "bert.encoder.layer.1.output.LayerNorm.weight",
+                   "bert.encoder.layer.0.attention.output.dense.weight", "bert.embeddings.position_embeddings.weight",
+                   "bert.embeddings.LayerNorm.bias", "cls.predictions.transform.dense_act.weight", "bert.pooler.dense_act.weight"]
+
+
 def main():
     from oracle import bert_oracle as O
     modeling = import_reference_modeling()
@@ -95,6 +101,23 @@ def main():
     r = run(modeling, tiny, sd, batch, capture_layers=True)
     torch.save(dict(cfg=tiny, state_dict=sd, batch=batch, **r), os.path.join(HERE, "bert_tiny_golden.pt"))
     print("tiny loss", float(r["loss"]))
+
+    # kernel-compatible small config (head size 64, H % 256 == 0, S % 128 == 0).  Weights are bf16-representable
+    # (rounded before use) so the bf16 GPU model and the fp32 reference hold identical parameters; they are
+    # regenerated from the seed by the tests, only outputs are stored.
+    small = dict(hidden_size=256, num_hidden_layers=2, num_attention_heads=4, intermediate_size=1024, vocab_size=1024,
+                 max_position_embeddings=128, type_vocab_size=2, hidden_act="gelu", initializer_range=0.02)
+    sd = O.bf16_representable_params(small, seed=21)
+    batch = O.synthetic_batch(2, 128, small["vocab_size"], 10, seed=5, full_mask=False)
+    r = run(modeling, small, sd, batch, capture_layers=True)
+    torch.save(dict(cfg=small, param_seed=21, batch_seed=5, loss=r["loss"], scores=r["scores"].half(), nsp=r["nsp"],
+                    seq_out=r["acts"]["layer1.out"].transpose(0, 1).contiguous().half(),
+                    layer0_ctx=r["acts"]["layer0.ctx"].transpose(0, 1).contiguous().half(),
+                    embeddings=r["acts"]["embeddings"].half(),
+                    grad_norms={k: v.norm() for k, v in r["grads"].items()},
+                    grads={k: r["grads"][k].half() for k in SMALL_GRAD_KEYS}),
+               os.path.join(HERE, "bert_small_golden.pt"))
+    print("small loss", float(r["loss"]))
 
     base = dict(O.BERT_BASE)
     sd = O.init_params(base, seed=42)

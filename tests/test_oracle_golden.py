@@ -81,3 +81,21 @@ def test_param_inventory_bert_large():
     shp = O.param_shapes(O.BERT_LARGE)
     n = sum(int(torch.tensor(s).prod()) for s in shp.values())
     assert len(shp) == 398 and n == 336_232_258
+
+
+def test_small_kernel_config_matches_reference(golden_dir):
+    """The config the GPU parity tests use (H=256, A=4 -> head 64, S=128): oracle == reference."""
+    gold = torch.load(os.path.join(golden_dir, "bert_small_golden.pt"), weights_only=False)
+    cfg = gold["cfg"]
+    sd = {k: v.clone().requires_grad_(True) for k, v in O.bf16_representable_params(cfg, seed=gold["param_seed"]).items()}
+    batch = O.synthetic_batch(2, 128, cfg["vocab_size"], 10, seed=gold["batch_seed"], full_mask=False)
+    loss, scores, nsp, seq = O.forward_loss(sd, cfg, batch)
+    torch.testing.assert_close(loss, gold["loss"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(scores, gold["scores"].float(), rtol=2e-3, atol=2e-3)
+    torch.testing.assert_close(seq, gold["seq_out"].float(), rtol=2e-3, atol=2e-3)
+    loss.backward()
+    for k, g in gold["grads"].items():
+        torch.testing.assert_close(sd[k].grad, g.float(), rtol=5e-3, atol=1e-5, msg=lambda m, k=k: f"{k}: {m}")
+    for k, n in gold["grad_norms"].items():
+        if k != "cls.predictions.decoder.weight":
+            assert float(sd[k].grad.norm()) == pytest.approx(float(n), rel=1e-3, abs=1e-6), k   # key.bias grad is analytically 0
