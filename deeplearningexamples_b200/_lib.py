@@ -61,6 +61,7 @@ SIGNATURES = {
     "dle_lamb_plan_create": (_i32, [ctypes.POINTER(LambTensor), _i32, ctypes.POINTER(LambGroup), _i32, _i32,
                                     ctypes.POINTER(_vp)]),
     "dle_lamb_plan_destroy": (_i32, [_vp]),
+    "dle_lamb_plan_update": (_i32, [_vp, ctypes.POINTER(LambTensor), _i32, _vp]),
     "dle_lamb_step": (_i32, [_vp, _vp, _f32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "dle_lamb_grad_norm": (_i32, [_vp, _vp, _vp, _vp]),
 }
@@ -69,6 +70,8 @@ _ERRORS = {-22: "DLE_ERR_INVALID (bad shape/alignment/null pointer)", -5: "DLE_E
            -38: "DLE_ERR_NOSYS (not compiled in)"}
 
 _lib = None
+# number of kernels of THIS library launched so far (bench.py reports it as gpu_launches)
+launch_count = {"n": 0}
 
 
 class DleError(RuntimeError):

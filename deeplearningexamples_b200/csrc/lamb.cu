@@ -43,6 +43,7 @@ struct LambPlan {                            // host-side handle
     void* block; size_t block_bytes;
     int n_tensors, n_groups, n_chunks, grad_dtype;
     long long total_numel;
+    void* host_stage = nullptr; long long* stage_numel = nullptr; cudaEvent_t stage_event = nullptr;
 };
 
 __device__ __forceinline__ float block_reduce_sum(float v, float* sh) {
@@ -317,10 +318,40 @@ extern "C" int dle_lamb_plan_create(const dle_lamb_tensor* ht, int32_t n_tensors
     return DLE_OK;
 }
 
+// Re-point an existing plan at new gradient / parameter addresses (same tensor count, sizes and groups): one small
+// H2D copy on `stream`, no allocation.  Autograd hands out fresh gradient tensors every step when the driver uses
+// zero_grad(set_to_none=True) (run_pretraining.py:536), so this is on the per-step path.
+extern "C" int dle_lamb_plan_update(void* plan, const dle_lamb_tensor* ht, int32_t n_tensors, void* stream) {
+    DLE_CHECK_ARG(plan && ht);
+    LambPlan* pl = static_cast<LambPlan*>(plan);
+    DLE_CHECK_ARG(n_tensors == pl->n_tensors);
+    if (pl->host_stage == nullptr) {
+        if (cudaMallocHost(&pl->host_stage, sizeof(LambTensorDev) * n_tensors) != cudaSuccess) return DLE_ERR_CUDA;
+        pl->stage_numel = new long long[n_tensors];
+        if (cudaMemcpy(pl->host_stage, pl->tensors, sizeof(LambTensorDev) * n_tensors, cudaMemcpyDeviceToHost) != cudaSuccess) return DLE_ERR_CUDA;
+        for (int i = 0; i < n_tensors; ++i) pl->stage_numel[i] = static_cast<LambTensorDev*>(pl->host_stage)[i].n;
+    }
+    LambTensorDev* t = static_cast<LambTensorDev*>(pl->host_stage);
+    // the staging buffer may still be in flight from the previous update on this stream
+    if (pl->stage_event && cudaEventSynchronize(pl->stage_event) != cudaSuccess) return DLE_ERR_CUDA;
+    for (int i = 0; i < n_tensors; ++i) {
+        DLE_CHECK_ARG(ht[i].numel == pl->stage_numel[i] && ht[i].grad && ht[i].param && ht[i].exp_avg && ht[i].exp_avg_sq);
+        t[i] = LambTensorDev{ht[i].grad, ht[i].param, ht[i].exp_avg, ht[i].exp_avg_sq, ht[i].model_param, ht[i].numel, ht[i].group, 0};
+    }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (cudaMemcpyAsync(pl->tensors, t, sizeof(LambTensorDev) * n_tensors, cudaMemcpyHostToDevice, s) != cudaSuccess) return DLE_ERR_CUDA;
+    if (!pl->stage_event && cudaEventCreateWithFlags(&pl->stage_event, cudaEventDisableTiming) != cudaSuccess) return DLE_ERR_CUDA;
+    if (cudaEventRecord(pl->stage_event, s) != cudaSuccess) return DLE_ERR_CUDA;
+    return DLE_OK;
+}
+
 extern "C" int dle_lamb_plan_destroy(void* plan) {
     DLE_CHECK_ARG(plan);
     LambPlan* pl = static_cast<LambPlan*>(plan);
     cudaFree(pl->block);
+    if (pl->host_stage) cudaFreeHost(pl->host_stage);
+    if (pl->stage_event) cudaEventDestroy(pl->stage_event);
+    delete[] pl->stage_numel;
     delete pl;
     return DLE_OK;
 }

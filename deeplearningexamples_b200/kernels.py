@@ -10,6 +10,8 @@ import torch
 from . import _lib as L
 
 bf16 = torch.bfloat16
+# when a list, gemm() brackets every launch with CUDA events on the launching stream: (e0, e1, flops, tag)
+gemm_profile = None
 
 
 def _stream():
@@ -71,7 +73,13 @@ def gemm(a, b, *, a_layout=L.LAYOUT_K, b_layout=L.LAYOUT_K, epilogue=L.EPI_BIAS,
     args.epilogue, args.splits, args.tile_n = epilogue, splits, tile_n
     args.alpha, args.dropout_p = alpha, dropout_p
     args.dropout_stream, args.seed = dropout_stream, seed
-    L.check(lib.dle_gemm_bf16(ctypes.byref(args), _stream()), "dle_gemm_bf16")
+    if gemm_profile is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    L.launch_count["n"] += 1; L.check(lib.dle_gemm_bf16(ctypes.byref(args), _stream()), "dle_gemm_bf16")
+    if gemm_profile is not None:
+        e1.record()
+        gemm_profile.append((e0, e1, 2.0 * M * N * K, (M, N, K, a_layout, b_layout, epilogue)))
     return (out, out2) if epilogue == L.EPI_BIAS_GELU else out
 
 
@@ -85,7 +93,7 @@ def attn_fwd(qkv, mask, B, S, A, dropout_p=0.0, seed=0, dropout_stream=0, seq_fi
     lse = torch.empty((B, A, S), device=qkv.device, dtype=torch.float32)
     if mask is not None:
         _req(mask, torch.float32, "mask")
-    L.check(lib.dle_attn_fwd(_ptr(qkv), _ptr(mask), _ptr(ctx), _ptr(lse), B, S, A, 1 if seq_first else 0, dropout_p, seed,
+    L.launch_count["n"] += 1; L.check(lib.dle_attn_fwd(_ptr(qkv), _ptr(mask), _ptr(ctx), _ptr(lse), B, S, A, 1 if seq_first else 0, dropout_p, seed,
                              dropout_stream, _stream()), "dle_attn_fwd")
     return ctx, lse
 
@@ -94,7 +102,7 @@ def attn_bwd(qkv, mask, ctx, dctx, lse, B, S, A, dropout_p=0.0, seed=0, dropout_
     lib = L.load()
     dqkv = torch.empty_like(qkv)
     delta = torch.empty((B, A, S), device=qkv.device, dtype=torch.float32)
-    L.check(lib.dle_attn_bwd(_ptr(qkv), _ptr(mask), _ptr(ctx), _ptr(_req(dctx, bf16, "dctx")), _ptr(lse), _ptr(dqkv),
+    L.launch_count["n"] += 2; L.check(lib.dle_attn_bwd(_ptr(qkv), _ptr(mask), _ptr(ctx), _ptr(_req(dctx, bf16, "dctx")), _ptr(lse), _ptr(dqkv),
                              _ptr(delta), B, S, A, 1 if seq_first else 0, dropout_p, seed, dropout_stream, _stream()), "dle_attn_bwd")
     return dqkv
 
@@ -112,7 +120,7 @@ def add_ln_fwd(x, gamma, beta, *, bias=None, residual=None, eps=1e-12, dropout_p
     y = torch.empty_like(x)
     mean = torch.empty(T, device=x.device, dtype=torch.float32)
     rstd = torch.empty(T, device=x.device, dtype=torch.float32)
-    L.check(lib.dle_add_ln_fwd(_ptr(x), _ptr(bias), _ptr(residual), _ptr(gamma), _ptr(beta), _ptr(z), _ptr(y), _ptr(mean),
+    L.launch_count["n"] += 1; L.check(lib.dle_add_ln_fwd(_ptr(x), _ptr(bias), _ptr(residual), _ptr(gamma), _ptr(beta), _ptr(z), _ptr(y), _ptr(mean),
                                _ptr(rstd), T, H, eps, dropout_p, seed, dropout_stream, _stream()), "dle_add_ln_fwd")
     return y, (z if z is not None else x), mean, rstd
 
@@ -125,13 +133,13 @@ def add_ln_bwd(dy, z, mean, rstd, gamma, *, dropout_p=0.0, seed=0, dropout_strea
     parts = torch.empty((3, n_part, H), device=dy.device, dtype=torch.float32)
     dz = torch.empty_like(dy)
     dx = torch.empty_like(dy) if dropout_p > 0.0 else None
-    L.check(lib.dle_add_ln_bwd(_ptr(dy), _ptr(z), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dz), _ptr(dx), _ptr(parts[0]),
+    L.launch_count["n"] += 1; L.check(lib.dle_add_ln_bwd(_ptr(dy), _ptr(z), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dz), _ptr(dx), _ptr(parts[0]),
                                _ptr(parts[1]), _ptr(parts[2]) if want_dbias else None, T, H, dropout_p, seed,
                                dropout_stream, _stream()), "dle_add_ln_bwd")
     outs = []
     for k in range(3 if want_dbias else 2):
         o = torch.empty(H, device=dy.device, dtype=torch.float32)
-        L.check(lib.dle_colsum_finalize(_ptr(parts[k]), n_part, H, _ptr(o), L.DLE_DTYPE_F32, 0, _stream()), "dle_colsum_finalize")
+        L.launch_count["n"] += 1; L.check(lib.dle_colsum_finalize(_ptr(parts[k]), n_part, H, _ptr(o), L.DLE_DTYPE_F32, 0, _stream()), "dle_colsum_finalize")
         outs.append(o)
     return (dz, dx if dx is not None else dz, *outs)
 
@@ -143,9 +151,9 @@ def colsum(x):
     T, N = x.shape
     n_part = lib.dle_colsum_partials(T)
     part = torch.empty((n_part, N), device=x.device, dtype=torch.float32)
-    L.check(lib.dle_colsum_bf16(_ptr(x), T, N, _row_major_2d(x, "x"), _ptr(part), _stream()), "dle_colsum_bf16")
+    L.launch_count["n"] += 1; L.check(lib.dle_colsum_bf16(_ptr(x), T, N, _row_major_2d(x, "x"), _ptr(part), _stream()), "dle_colsum_bf16")
     out = torch.empty(N, device=x.device, dtype=torch.float32)
-    L.check(lib.dle_colsum_finalize(_ptr(part), n_part, N, _ptr(out), L.DLE_DTYPE_F32, 0, _stream()), "dle_colsum_finalize")
+    L.launch_count["n"] += 1; L.check(lib.dle_colsum_finalize(_ptr(part), n_part, N, _ptr(out), L.DLE_DTYPE_F32, 0, _stream()), "dle_colsum_finalize")
     return out
 
 
@@ -155,7 +163,7 @@ def bias_gelu_fwd(x, bias=None, save_u=True):
     T, N = x.shape
     u = torch.empty_like(x) if (save_u and bias is not None) else None
     y = torch.empty_like(x)
-    L.check(lib.dle_bias_gelu_fwd(_ptr(x), _ptr(bias), _ptr(u), _ptr(y), T, N, _stream()), "dle_bias_gelu_fwd")
+    L.launch_count["n"] += 1; L.check(lib.dle_bias_gelu_fwd(_ptr(x), _ptr(bias), _ptr(u), _ptr(y), T, N, _stream()), "dle_bias_gelu_fwd")
     return y, (u if u is not None else x)
 
 
@@ -163,7 +171,7 @@ def bias_gelu_bwd(dy, u):
     lib = L.load()
     T, N = dy.shape
     du = torch.empty_like(dy)
-    L.check(lib.dle_bias_gelu_bwd(_ptr(dy), _ptr(u), _ptr(du), T, N, _stream()), "dle_bias_gelu_bwd")
+    L.launch_count["n"] += 1; L.check(lib.dle_bias_gelu_bwd(_ptr(dy), _ptr(u), _ptr(du), T, N, _stream()), "dle_bias_gelu_bwd")
     return du
 
 
@@ -181,7 +189,7 @@ def embed_ln_fwd(input_ids, token_type_ids, word, pos, typ, gamma, beta, *, eps=
     y = torch.empty((T, H), device=word.device, dtype=bf16)
     mean = torch.empty(T, device=word.device, dtype=torch.float32)
     rstd = torch.empty(T, device=word.device, dtype=torch.float32)
-    L.check(lib.dle_embed_ln_fwd(_ptr(input_ids), _ptr(token_type_ids), _ptr(word), _ptr(pos), _ptr(typ), _ptr(gamma), _ptr(beta),
+    L.launch_count["n"] += 1; L.check(lib.dle_embed_ln_fwd(_ptr(input_ids), _ptr(token_type_ids), _ptr(word), _ptr(pos), _ptr(typ), _ptr(gamma), _ptr(beta),
                                  _ptr(z), _ptr(y), _ptr(mean), _ptr(rstd), B, S, H, word.shape[0], pos.shape[0], typ.shape[0],
                                  eps, dropout_p, seed, dropout_stream, _ptr(err_flag), _stream()), "dle_embed_ln_fwd")
     return y, z, mean, rstd
@@ -197,13 +205,13 @@ def embed_ln_bwd(dy, z, mean, rstd, gamma, input_ids, token_type_ids, V, P, NT, 
     dtyp = torch.zeros((NT, H), device=dy.device, dtype=torch.float32)
     n_part = lib.dle_ln_bwd_partials(T)
     parts = torch.empty((2, n_part, H), device=dy.device, dtype=torch.float32)
-    L.check(lib.dle_embed_ln_bwd(_ptr(dy), _ptr(z), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(input_ids), _ptr(token_type_ids),
+    L.launch_count["n"] += 1; L.check(lib.dle_embed_ln_bwd(_ptr(dy), _ptr(z), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(input_ids), _ptr(token_type_ids),
                                  _ptr(dword), _ptr(dpos), _ptr(dtyp), _ptr(parts[0]), _ptr(parts[1]), B, S, H, dropout_p, seed,
                                  dropout_stream, _stream()), "dle_embed_ln_bwd")
     outs = []
     for k in range(2):
         o = torch.empty(H, device=dy.device, dtype=torch.float32)
-        L.check(lib.dle_colsum_finalize(_ptr(parts[k]), n_part, H, _ptr(o), L.DLE_DTYPE_F32, 0, _stream()), "dle_colsum_finalize")
+        L.launch_count["n"] += 1; L.check(lib.dle_colsum_finalize(_ptr(parts[k]), n_part, H, _ptr(o), L.DLE_DTYPE_F32, 0, _stream()), "dle_colsum_finalize")
         outs.append(o)
     return dword, dpos, dtyp, outs[0], outs[1]
 
@@ -214,7 +222,7 @@ def gather_rows(x, idx, err_flag=None):
     out = torch.empty((idx.numel(), x.shape[1]), device=x.device, dtype=bf16)
     if idx.numel() == 0:
         return out
-    L.check(lib.dle_gather_rows(_ptr(x), _ptr(idx), _ptr(out), idx.numel(), x.shape[1], x.shape[0], _ptr(err_flag), _stream()),
+    L.launch_count["n"] += 1; L.check(lib.dle_gather_rows(_ptr(x), _ptr(idx), _ptr(out), idx.numel(), x.shape[1], x.shape[0], _ptr(err_flag), _stream()),
             "dle_gather_rows")
     return out
 
@@ -224,7 +232,7 @@ def scatter_rows(dy, idx, n_rows):
     dx = torch.zeros((n_rows, dy.shape[1]), device=dy.device, dtype=bf16)
     if idx.numel() == 0:
         return dx
-    L.check(lib.dle_scatter_rows(_ptr(dy), _ptr(idx), _ptr(dx), idx.numel(), dy.shape[1], n_rows, _stream()), "dle_scatter_rows")
+    L.launch_count["n"] += 1; L.check(lib.dle_scatter_rows(_ptr(dy), _ptr(idx), _ptr(dx), idx.numel(), dy.shape[1], n_rows, _stream()), "dle_scatter_rows")
     return dx
 
 
@@ -232,7 +240,7 @@ def cast_f32_to_bf16(x, out=None):
     lib = L.load()
     _req(x, torch.float32, "x")
     out = torch.empty(x.shape, device=x.device, dtype=bf16) if out is None else out
-    L.check(lib.dle_cast_f32_to_bf16(_ptr(x), _ptr(out), x.numel(), _stream()), "dle_cast_f32_to_bf16")
+    L.launch_count["n"] += 1; L.check(lib.dle_cast_f32_to_bf16(_ptr(x), _ptr(out), x.numel(), _stream()), "dle_cast_f32_to_bf16")
     return out
 
 
@@ -240,5 +248,5 @@ def cast_bf16_to_f32(x, out=None):
     lib = L.load()
     _req(x, bf16, "x")
     out = torch.empty(x.shape, device=x.device, dtype=torch.float32) if out is None else out
-    L.check(lib.dle_cast_bf16_to_f32(_ptr(x), _ptr(out), x.numel(), _stream()), "dle_cast_bf16_to_f32")
+    L.launch_count["n"] += 1; L.check(lib.dle_cast_bf16_to_f32(_ptr(x), _ptr(out), x.numel(), _stream()), "dle_cast_bf16_to_f32")
     return out

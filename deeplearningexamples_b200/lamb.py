@@ -196,11 +196,21 @@ class FusedLAMBAMP(torch.optim.Optimizer):
         if self._plan is not None and self._plan_sig is not None and self._plan_sig[0] == gsig:
             return
         built, sig = self._build_plan()
-        self._drop_plan()
         if built is None:
+            self._drop_plan()
             return
         tensors, groups, gdt = built
         tarr = (L.LambTensor * len(tensors))(*tensors)
+        shape_sig = (gdt, tuple((t.numel, t.group) for t in tensors),
+                     tuple((g.step, g.beta1, g.beta2, g.eps, g.weight_decay, g.bias_correction, g.grad_averaging) for g in groups))
+        if self._plan is not None and getattr(self, "_plan_shape_sig", None) == shape_sig:
+            # only addresses moved (fresh .grad tensors after zero_grad(set_to_none=True)): patch the device table
+            L.check(L.load().dle_lamb_plan_update(self._plan, tarr, len(tensors),
+                                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "dle_lamb_plan_update")
+            self._plan_sig = (gsig, sig)
+            return
+        self._drop_plan()
+        self._plan_shape_sig = shape_sig
         garr = (L.LambGroup * len(groups))(*groups)
         plan = ctypes.c_void_p()
         L.check(L.load().dle_lamb_plan_create(tarr, len(tensors), garr, len(groups), gdt, ctypes.byref(plan)),
@@ -233,6 +243,7 @@ class FusedLAMBAMP(torch.optim.Optimizer):
                                        1 if self.use_nvlamb else 0, ctypes.c_void_p(self._found_inf.data_ptr()),
                                        ctypes.c_void_p(self._global_grad_norm.data_ptr()), ctypes.c_void_p(0), stream),
                 "dle_lamb_step")
+        L.launch_count["n"] += 3
         from . import ops
         ops.weight_epoch["n"] += 1          # parameters changed through raw pointers: invalidate cached bf16 copies
         if grad_scaler is not None and grad_scaler.is_enabled():

@@ -1,0 +1,123 @@
+"""Training-step glue mirroring the reference driver's functions
+(PyTorch/LanguageModeling/BERT/run_pretraining.py) so bench.py, smoke() and the tests execute the same
+sequence the reference's main loop does:
+
+  BertPretrainingCriterion   run_pretraining.py:75-95
+  prepare_model_and_optimizer  :377-486  (param groups :422-427, FusedLAMBAMP :429, scheduler :431-435,
+                                          GradScaler :436, DDP wrap :455-458, setup_fp32_params :477)
+  take_training_step         :518-524
+  take_optimizer_step        :527-536
+  synthetic_batch            the lddl batch format read at :520-521,603-609 (five int64 tensors)
+
+Differences: bf16 instead of fp16 (`model.bfloat16()` where the reference does `model.half()` for
+--allreduce_post_accumulation_fp16); DDP uses overlap-sized buckets instead of one bucket of total_memory MB.
+"""
+import torch
+
+from . import modeling
+from .lamb import FusedLAMBAMP
+from .schedulers import PolyWarmUpScheduler
+
+BERT_LARGE = dict(attention_probs_dropout_prob=0.1, hidden_act="gelu", hidden_dropout_prob=0.1, hidden_size=1024,
+                  initializer_range=0.02, intermediate_size=4096, max_position_embeddings=512, num_attention_heads=16,
+                  num_hidden_layers=24, type_vocab_size=2, vocab_size=30522)
+BERT_BASE = dict(attention_probs_dropout_prob=0.1, hidden_act="gelu", hidden_dropout_prob=0.1, hidden_size=768,
+                 initializer_range=0.02, intermediate_size=3072, max_position_embeddings=512, num_attention_heads=12,
+                 num_hidden_layers=12, type_vocab_size=2, vocab_size=30528)
+
+# training FLOPs per sequence (SURVEY.md 8d / BASELINE.md 2): 3 x forward, GEMM + attention contractions only
+def train_flops_per_seq(cfg, S, P):
+    L_, H, I, V = cfg["num_hidden_layers"], cfg["hidden_size"], cfg["intermediate_size"], cfg["vocab_size"]
+    fwd = L_ * (6 * S * H * H + 4 * S * S * H + 2 * S * H * H + 4 * S * H * I) + (2 * P * H * H + 2 * P * H * V + 2 * H * H)
+    return 3 * fwd
+
+
+class BertPretrainingCriterion(torch.nn.Module):
+    def __init__(self, vocab_size, sequence_output_is_dense=False):
+        super().__init__()
+        self.loss_fn = torch.nn.CrossEntropyLoss(ignore_index=-1)
+        self.vocab_size = vocab_size
+        self.sequence_output_is_dense = sequence_output_is_dense
+
+    def forward(self, prediction_scores, seq_relationship_score, masked_lm_labels, next_sentence_labels):
+        if self.sequence_output_is_dense:
+            flat = masked_lm_labels.view(-1)
+            mlm_labels = flat[flat != -1]
+            masked_lm_loss = self.loss_fn(prediction_scores.view(-1, self.vocab_size), mlm_labels.view(-1))
+        else:
+            masked_lm_loss = self.loss_fn(prediction_scores.view(-1, self.vocab_size), masked_lm_labels.view(-1))
+        next_sentence_loss = self.loss_fn(seq_relationship_score.view(-1, 2), next_sentence_labels.view(-1))
+        return masked_lm_loss + next_sentence_loss
+
+
+def synthetic_batch(B, S, vocab, max_pred, seed=42, full_mask=True, device="cpu", pin=False):
+    """ids ~ U{0..30521} with [CLS] first, segment split at S/2, exactly max_pred labels per row."""
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(0, min(vocab, 30522), (B, S), generator=g, dtype=torch.int64)
+    ids[:, 0] = 101
+    tt = torch.zeros(B, S, dtype=torch.int64)
+    tt[:, S // 2:] = 1
+    if full_mask:
+        am = torch.ones(B, S, dtype=torch.int64)
+    else:
+        lens = (torch.randint(S // 4, S + 1, (B,), generator=g) + 63) // 64 * 64
+        am = (torch.arange(S).unsqueeze(0) < lens.clamp(max=S).unsqueeze(1)).to(torch.int64)
+    labels = torch.full((B, S), -1, dtype=torch.int64)
+    for b in range(B):
+        pos = torch.randperm(S, generator=g)[:max_pred]
+        labels[b, pos] = torch.randint(0, min(vocab, 30522), (max_pred,), generator=g)
+    nsl = torch.randint(0, 2, (B,), generator=g, dtype=torch.int64)
+    batch = {"input_ids": ids, "token_type_ids": tt, "attention_mask": am, "labels": labels, "next_sentence_labels": nsl}
+    if pin:
+        batch = {k: v.pin_memory() for k, v in batch.items()}
+    if device != "cpu":
+        batch = {k: v.to(device) for k, v in batch.items()}
+    return batch
+
+
+def prepare_model_and_optimizer(config_dict, device, *, learning_rate=6e-3, warmup_proportion=0.2843, max_steps=7038,
+                                sequence_output_is_dense=True, init_loss_scale=2 ** 20, use_grad_scaler=True,
+                                distributed=False, bucket_cap_mb=100, dtype=torch.bfloat16, seed=42):
+    cfg = dict(config_dict)
+    if cfg["vocab_size"] % 8 != 0:                       # run_pretraining.py:383-384
+        cfg["vocab_size"] += 8 - (cfg["vocab_size"] % 8)
+    config = modeling.BertConfig.from_dict(cfg)
+    torch.manual_seed(seed)
+    model = modeling.BertForPreTraining(config, sequence_output_is_dense=sequence_output_is_dense)
+    model.to(device)
+    model.to(dtype)                                       # the reference's model.half() (:416-417), in bf16
+    no_decay = ['bias', 'gamma', 'beta', 'LayerNorm']     # :422-427
+    named = list(model.named_parameters())
+    groups = [{'params': [p for n, p in named if not any(nd in n for nd in no_decay)], 'weight_decay': 0.01},
+              {'params': [p for n, p in named if any(nd in n for nd in no_decay)], 'weight_decay': 0.0}]
+    optimizer = FusedLAMBAMP(groups, lr=learning_rate)
+    lr_scheduler = PolyWarmUpScheduler(optimizer, warmup=warmup_proportion, total_steps=max_steps,
+                                       base_lr=learning_rate, device=device)
+    grad_scaler = torch.amp.GradScaler("cuda", init_scale=init_loss_scale, enabled=use_grad_scaler)
+    if distributed:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            model = DDP(model, device_ids=[device.index], output_device=device.index, bucket_cap_mb=bucket_cap_mb,
+                        gradient_as_bucket_view=True)
+        torch.cuda.current_stream().wait_stream(side)
+    optimizer.setup_fp32_params()                          # :477 (after the DDP wrap, as in the reference)
+    criterion = BertPretrainingCriterion(config.vocab_size, sequence_output_is_dense=sequence_output_is_dense)
+    return model, optimizer, grad_scaler, lr_scheduler, criterion, config
+
+
+def take_training_step(grad_scaler, model, criterion, batch, loss_acc=None):
+    prediction_scores, seq_relationship_score = model(input_ids=batch['input_ids'], token_type_ids=batch['token_type_ids'],
+                                                      attention_mask=batch['attention_mask'], masked_lm_labels=batch['labels'])
+    loss = criterion(prediction_scores, seq_relationship_score, batch['labels'], batch['next_sentence_labels'])
+    if loss_acc is not None:
+        loss_acc.add_(loss.detach().float())
+    grad_scaler.scale(loss).backward()
+    return loss
+
+
+def take_optimizer_step(lr_scheduler, optimizer, grad_scaler):
+    lr_scheduler.step()
+    grad_scaler.step(optimizer)
+    grad_scaler.update()
+    optimizer.zero_grad(set_to_none=True)

@@ -112,9 +112,7 @@ int dle_add_ln_fwd(const void* x, const void* bias, const void* residual, const 
                    void* z_out, void* y, float* mean, float* rstd, int64_t T, int32_t H, float eps,
                    float dropout_p, uint64_t seed, uint32_t dropout_stream, void* stream);
 /* backward: dz = dLN(dy); dx = dropout_bwd(dz) written to dx_out when dropout_p > 0 (else dx == dz
- * and dx_out may be NULL).  If dz_add != NULL it is added into dz first-class (the gradient arriving
- * through the other consumer of y is NOT this; dz_add is the extra gradient of z's residual branch).
- * Column reductions are written as fp32 partials [n_part, H] into the caller's workspace:
+ * and dx_out may be NULL).  dz is also the gradient of the residual branch.  Column reductions are written as fp32 partials [n_part, H] into the caller's workspace:
  *   part_dgamma, part_dbeta, part_dbias (sum_t dx).  n_part = dle_ln_bwd_partials(T).  A second
  *   call dle_colsum_finalize reduces them to bf16/fp32 gradients. */
 int dle_ln_bwd_partials(int64_t T);
@@ -197,6 +195,8 @@ typedef struct dle_lamb_group {
 int dle_lamb_plan_create(const dle_lamb_tensor* host_tensors, int32_t n_tensors, const dle_lamb_group* host_groups,
                          int32_t n_groups, int32_t grad_dtype, void** plan_out);
 int dle_lamb_plan_destroy(void* plan);
+/* re-point the plan at new grad/param addresses (same tensor count, sizes, groups); one small async H2D copy */
+int dle_lamb_plan_update(void* plan, const dle_lamb_tensor* host_tensors, int32_t n_tensors, void* stream);
 /* scale: device fp32 loss scale or NULL (=1).  found_inf_out / global_grad_norm_out: device fp32
  * scalars written by the call (global_grad_norm is the norm of the SCALED grads, as in the reference).
  * per_tensor_norms_out: optional device fp32 [2*n_tensors] (param norms then update norms). */

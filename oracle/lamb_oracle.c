@@ -27,6 +27,7 @@
 int lamb_oracle_sumsq_f32(const float* x, int64_t n, double* out)
 {
     double s = 0.0; int bad = 0;
+#pragma omp parallel for reduction(+:s) reduction(|:bad) if (n > 65536)
     for (int64_t i = 0; i < n; ++i) { float f = x[i]; if (!isfinite(f)) bad = 1; s += (double)f * (double)f; }
     *out = s; return bad;
 }
@@ -40,6 +41,7 @@ double lamb_oracle_stage1_f32(const float* g, const float* p, float* m, float* v
                               int mode, float decay, float clipped_global_grad_norm, float inv_scale)
 {
     double usq = 0.0;
+#pragma omp parallel for reduction(+:usq) if (n > 65536)
     for (int64_t i = 0; i < n; ++i) {
         float r_g = g[i] * inv_scale;
         float r_p = (decay == 0.0f) ? 0.0f : p[i];
@@ -71,5 +73,6 @@ void lamb_oracle_stage2_f32(float* p, const float* update, int64_t n, float lr,
     float ratio = lr;
     if (use_nvlamb || decay != 0.0f)
         ratio = (update_norm != 0.0f && param_norm != 0.0f) ? lr * (param_norm / update_norm) : lr;
+#pragma omp parallel for if (n > 65536)
     for (int64_t i = 0; i < n; ++i) p[i] = p[i] - ratio * update[i];
 }

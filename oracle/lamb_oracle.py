@@ -17,11 +17,11 @@ _lib = None
 
 
 def build(force=False):
-    """gcc -O2 -shared oracle/lamb_oracle.c -> oracle/liblamb_oracle.so (no -ffast-math:
+    """gcc -O2 -fopenmp -shared oracle/lamb_oracle.c -> oracle/liblamb_oracle.so (no -ffast-math:
     the oracle keeps IEEE division/sqrt)."""
     src = os.path.join(_HERE, "lamb_oracle.c")
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-o", _SO, src, "-lm"])
+        subprocess.check_call(["gcc", "-O2", "-fopenmp", "-fPIC", "-shared", "-o", _SO, src, "-lm"])
     return _SO
 
 

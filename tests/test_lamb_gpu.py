@@ -137,3 +137,64 @@ def test_lamb_full_bert_large_shape_list_properties():
             assert torch.equal(m1, m0)
     for p, m in zip(decay + nodecay, masters1):
         assert torch.equal(p.data, m.to(torch.bfloat16))
+
+
+def _ref_ext():
+    from oracle import build_ref
+    return build_ref.load_module()
+
+
+def test_oracle_vs_reference_kernel():
+    """Pins the CPU oracle (and our kernel) to the reference's OWN CUDA kernels, rebuilt from /root/reference into
+    oracle/_ref: fused_lamb_CUDA.multi_tensor_l2norm / multi_tensor_lamb driven exactly as fused_lamb.py:166-258 does."""
+    ext = _ref_ext()
+    if ext is None:
+        pytest.skip("oracle/_ref/fused_lamb_CUDA.so not present")
+    from deeplearningexamples_b200.lamb import FusedLAMBAMP
+    from oracle import lamb_oracle as LO
+    rng = np.random.default_rng(5)
+    shapes = [(1024, 512), (300, 7), (4096,), (2,)]
+    host_p = [rng.standard_normal(s).astype(np.float32) * 0.05 for s in shapes]
+    wd, lr, scale = 0.01, 3e-3, 1024.0
+    # --- reference kernel state
+    rp = [torch.from_numpy(a.copy()).cuda() for a in host_p]
+    rm, rv = [torch.zeros_like(a) for a in rp], [torch.zeros_like(a) for a in rp]
+    rstep = torch.zeros(1, dtype=torch.int, device="cuda")
+    noop = torch.zeros(1, dtype=torch.int, device="cuda")
+    lr_t = torch.tensor(lr, device="cuda")
+    # --- ours
+    ours = [torch.nn.Parameter(torch.from_numpy(a.copy()).cuda()) for a in host_p]
+    opt = FusedLAMBAMP([{'params': ours, 'weight_decay': wd}], lr=lr)
+    opt.setup_fp32_params()
+    scaler = torch.amp.GradScaler("cuda", init_scale=scale, growth_interval=10 ** 9)
+    scaler._lazy_init_scale_growth_tracker(torch.device("cuda"))
+    # --- oracle
+    og = [dict(params=[a.copy() for a in host_p], grads=None, exp_avg=[np.zeros_like(a) for a in host_p],
+               exp_avg_sq=[np.zeros_like(a) for a in host_p], lr=lr, betas=(0.9, 0.999), eps=1e-6, weight_decay=wd, step=0,
+               bias_correction=True, grad_averaging=True)]
+    for it in range(3):
+        gs = [(rng.standard_normal(s).astype(np.float32) * (5.0 if it == 1 else 1e-2) * scale) for s in shapes]
+        rg = [torch.from_numpy(g.copy()).cuda() for g in gs]
+        for p, g in zip(ours, gs):
+            p.grad = torch.from_numpy(g.copy()).cuda()
+        og[0]["grads"] = [g.copy() for g in gs]
+        # reference host sequence (fused_lamb.py:148-258), fp32 4-list form
+        found_inf = torch.zeros(1, device="cuda")
+        sc = torch.full((1,), scale, device="cuda")
+        inv_scale = sc.double().reciprocal().float()
+        gnorm = ext.multi_tensor_l2norm(65536, noop, [rg], False)[0]
+        rstep += (noop != 1).int()
+        ext.multi_tensor_lamb(65536, noop, [rg, rp, rm, rv], lr_t, 0.9, 0.999, 1e-6, rstep, 1, wd, 1, 1, gnorm, 1.0 * sc, False,
+                              found_inf, inv_scale)
+        opt.step(grad_scaler=scaler)
+        LO.lamb_step(og, scale=scale)
+        assert gnorm.item() == pytest.approx(og[0] and LO.sumsq(np.concatenate([g.ravel() for g in gs]))[0] ** 0.5, rel=1e-5)
+    for i in range(len(shapes)):
+        # reference kernel is built with --use_fast_math (approximate div/sqrt): compare at 1e-4 to the IEEE oracle,
+        # ours at 1e-5 (north_star tolerance on fp32 LAMB moments)
+        np.testing.assert_allclose(rm[i].cpu().numpy(), og[0]["exp_avg"][i], rtol=1e-4, atol=1e-9)
+        np.testing.assert_allclose(rv[i].cpu().numpy(), og[0]["exp_avg_sq"][i], rtol=1e-4, atol=1e-12)
+        np.testing.assert_allclose(rp[i].cpu().numpy(), og[0]["params"][i], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(opt.state[ours[i]]['exp_avg'].cpu().numpy(), og[0]["exp_avg"][i], rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(opt.state[ours[i]]['exp_avg_sq'].cpu().numpy(), og[0]["exp_avg_sq"][i], rtol=1e-5, atol=1e-12)
+        np.testing.assert_allclose(ours[i].detach().cpu().numpy(), og[0]["params"][i], rtol=1e-5, atol=1e-7)
