@@ -22,6 +22,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "training_sequences_per_second"
+_T0 = time.time()
+
+
+def log(msg):
+    print(f"[bench +{time.time() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
 
 
 def parse():
@@ -117,11 +122,14 @@ def cpu_reference_run(cfg, S, P, ref_batch, steps, warmup):
             sd[k].grad = None
         return loss.item()
 
+    log(f"cpu arm: params built, {torch.get_num_threads()} threads")
     for i in range(warmup):
         step(i)
+        log(f"cpu warm-up {i} done")
     t0 = time.perf_counter()
     for i in range(steps):
         step(i)
+        log(f"cpu step {i} done")
     dt = time.perf_counter() - t0
     return dict(value=ref_batch * steps / dt, ms_per_step=1000.0 * dt / steps, cores=os.cpu_count(), threads=torch.get_num_threads(),
                 sample=f"{steps} steps x {ref_batch} sequences (S={S}) of the same workload after {warmup} warm-up; fp32 torch-CPU "
@@ -230,9 +238,14 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
+    log(f"model built: B={B} S={S} world={world}")
     for i in range(max(args.warmup, 3)):
         step_resident(i)
+        torch.cuda.synchronize()
+        log(f"warm-up step {i} done")
     step_e2e(0)
+    torch.cuda.synchronize()
+    log("warm-up done")
     sampler = ClockSampler(local) if rank == 0 else None
     t_start = time.time()
     if sampler:
@@ -240,9 +253,11 @@ def run_ours(args):
         time.sleep(0.3)
     n0 = L.launch_count["n"]
     ms_res = timed(step_resident, args.steps)
+    log(f"resident pass: {ms_res / args.steps:.2f} ms/step")
     launches = L.launch_count["n"] - n0
     K.gemm_profile = []
     ms_e2e = timed(step_e2e, args.steps)
+    log(f"e2e pass: {ms_e2e / args.steps:.2f} ms/step")
     prof, K.gemm_profile = K.gemm_profile, None
     t_end = time.time()
     clocks = sampler.stop(t_start, t_end) if sampler else None
@@ -278,7 +293,9 @@ def run_ours(args):
     if rank == 0 and n == 1 and not args.no_cpu_baseline:
         del model, opt
         torch.cuda.empty_cache()
+        log("cpu baseline ...")
         r = cpu_reference_run(cfg, S, P, args.ref_batch or 2, 2, 1)
+        log("cpu baseline done")
         line["cpu_baseline"] = {"value": round(r["value"], 4), "unit": "sequences/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
     if rank == 0:
         print(json.dumps(line), flush=True)

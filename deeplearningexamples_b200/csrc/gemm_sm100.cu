@@ -393,9 +393,10 @@ extern "C" int dle_gemm_bf16(const dle_gemm_args* a, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     DLE_CHECK_ARG(a != nullptr && a->A != nullptr && a->B != nullptr && a->out != nullptr);
     DLE_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0);
-    DLE_CHECK_ARG(a->N % 8 == 0 && a->K % 8 == 0 && a->ldo % 8 == 0);
+    // N % 8: the epilogue stores 16-byte vectors; lda/ldb % 8: TMA row strides are multiples of 16 bytes.
+    // M and K are otherwise free (TMA zero-fills out-of-bounds rows/columns of partial tiles).
+    DLE_CHECK_ARG(a->N % 8 == 0 && a->ldo % 8 == 0 && a->lda % 8 == 0 && a->ldb % 8 == 0);
     DLE_CHECK_ARG(a->epilogue >= 0 && a->epilogue < DLE_EPI_COUNT);
-    if (a->a_layout == DLE_LAYOUT_MN) DLE_CHECK_ARG(a->M % 8 == 0);
     if (a->epilogue == DLE_EPI_BIAS_GELU) DLE_CHECK_ARG(a->out2 != nullptr && a->ldo2 % 8 == 0);
     if (a->epilogue == DLE_EPI_DGELU || a->epilogue == DLE_EPI_ADD) DLE_CHECK_ARG(a->aux != nullptr);
     if (a->aux != nullptr) DLE_CHECK_ARG(a->ld_aux % 8 == 0);

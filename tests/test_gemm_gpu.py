@@ -135,9 +135,22 @@ def test_linearity_full_size():
     assert (err <= bound + 1e-3 * o3.abs()).all()
 
 
+def test_small_and_ragged_reduction_dims():
+    """wgrad of the pooler / MLM head: the reduction dim is a row count (B or N_mask), any value."""
+    k, L = _k()
+    for rows in (2, 20, 33):
+        dy, x = _rand((rows, 256), seed=31), _rand((rows, 512), seed=32)
+        out = k.gemm(dy, x, a_layout=L.LAYOUT_MN, b_layout=L.LAYOUT_MN, epilogue=L.EPI_F32)
+        torch.testing.assert_close(out, dy.float().t() @ x.float(), rtol=1e-3, atol=1e-2)
+    a, w = _rand((20, 264), seed=33), _rand((512, 264), 0.05, seed=34)     # K = 264: partial last k-block
+    _close(k.gemm(a, w), a.float() @ w.float().t())
+    xs = _rand((4, 128, 256), seed=35)[:, 0]                                # strided rows (hidden_states[:, 0])
+    _close(k.gemm(xs, _rand((256, 256), 0.05, seed=36)), xs.float() @ _rand((256, 256), 0.05, seed=36).float().t())
+
+
 def test_invalid_args_return_error():
     k, L = _k()
-    a, b = _rand((128, 60), seed=29), _rand((128, 60), seed=30)   # K % 8 != 0
+    a, b = _rand((128, 60), seed=29), _rand((128, 60), seed=30)   # row stride not a multiple of 16 bytes
     with pytest.raises(L.DleError):
         k.gemm(a, b)
     with pytest.raises(L.DleError):
