@@ -1,6 +1,6 @@
 // Dense bf16 GEMM for sm_100a: tcgen05.mma (cta_group::1, M=128) with fp32 accumulators in TMEM,
 // operands staged by TMA into 128B-swizzled shared memory, persistent warp-specialised CTAs
-// (1 TMA producer warp, 1 MMA issuer warp, 4 epilogue warps), double-buffered accumulators so the
+// (1 TMA producer warp, 1 MMA issuer warp, 8 epilogue warps), double-buffered accumulators so the
 // epilogue of tile i overlaps the main loop of tile i+1.
 //
 //   D[M,N] = A[M,K] * B[N,K]^T     (K = reduction)
@@ -21,7 +21,8 @@ namespace dle {
 constexpr int BM = 128;
 constexpr int BK = 64;        // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;      // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
+constexpr int GEMM_EPI_THREADS = 256;
 
 template <int BN> struct GemmCfg {
     static constexpr int A_BYTES = BM * BK * 2;
@@ -189,7 +190,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 128); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], GEMM_EPI_THREADS); }
         fence_barrier_init();
     }
     if (warp == 2) { tmem_alloc(tmem_ptr, Cfg::TMEM_COLS); tmem_relinquish(); }
@@ -268,7 +269,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
     } else if (warp >= 4) {
         // ===================== epilogue warps (TMEM -> registers -> global) =====================
-        const int q = warp & 3;                          // TMEM lane quarter owned by this warp
+        const int q = warp & 3;                          // TMEM lane quarter this warp may access
+        const int half = (warp - 4) >> 2;                // two warps share a quarter: each drains half the columns
         int it = 0;
         for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
             const int tile = unit / p.splits;
@@ -279,7 +281,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const long long row = (long long)m_blk * BM + q * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
                 uint32_t r[32];
                 tmem_ld32(taddr + c * 32, r);
                 tmem_ld_wait();

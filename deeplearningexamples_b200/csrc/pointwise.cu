@@ -187,18 +187,39 @@ add_ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, const
     }
 }
 
-// out[n] = sum_p part[p][n]
-__global__ void colsum_finalize_kernel(const float* __restrict__ part, int n_part, int N, void* out, int out_dtype, int accumulate) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
+// out[a][n] = sum_p part[a][p][n]   (grid: (ceil(N/32), n_arrays); 16 warps stride over the partial rows, each
+// warp reading 128 contiguous bytes per row; cross-warp reduction through shared memory)
+constexpr int CF_WARPS = 16;
+__global__ void __launch_bounds__(CF_WARPS * 32)
+colsum_finalize_kernel(const float* __restrict__ part, int n_part, int N, void* out, int out_dtype, int accumulate) {
+    __shared__ float red[CF_WARPS][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + lane;
+    const float* src = part + (long long)blockIdx.y * n_part * N;
     float s = 0.f;
-    for (int p = 0; p < n_part; ++p) s += part[(long long)p * N + n];
-    if (out_dtype == DLE_DTYPE_F32) {
-        float* o = reinterpret_cast<float*>(out);
-        o[n] = accumulate ? o[n] + s : s;
-    } else {
-        bf16* o = reinterpret_cast<bf16*>(out);
-        o[n] = __float2bfloat16_rn(accumulate ? __bfloat162float(o[n]) + s : s);
+    if (n < N) {
+        int p = warp;
+        for (; p + 3 * CF_WARPS < n_part; p += 4 * CF_WARPS) {
+            const float a = src[(long long)p * N + n], b = src[(long long)(p + CF_WARPS) * N + n];
+            const float c = src[(long long)(p + 2 * CF_WARPS) * N + n], d = src[(long long)(p + 3 * CF_WARPS) * N + n];
+            s += (a + b) + (c + d);
+        }
+        for (; p < n_part; p += CF_WARPS) s += src[(long long)p * N + n];
+    }
+    red[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0 && n < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < CF_WARPS; ++w) t += red[w][lane];
+        const long long o_idx = (long long)blockIdx.y * N + n;
+        if (out_dtype == DLE_DTYPE_F32) {
+            float* o = reinterpret_cast<float*>(out);
+            o[o_idx] = accumulate ? o[o_idx] + t : t;
+        } else {
+            bf16* o = reinterpret_cast<bf16*>(out);
+            o[o_idx] = __float2bfloat16_rn(accumulate ? __bfloat162float(o[o_idx]) + t : t);
+        }
     }
 }
 
@@ -499,8 +520,12 @@ extern "C" int dle_add_ln_bwd(const void* dy, const void* z, const float* mean, 
 
 extern "C" int dle_colsum_finalize(const float* part, int32_t n_part, int32_t N, void* out, int32_t out_dtype,
                                    int32_t accumulate, void* stream) {
-    DLE_CHECK_ARG(part && out && n_part > 0 && N > 0 && (out_dtype == DLE_DTYPE_F32 || out_dtype == DLE_DTYPE_BF16));
-    colsum_finalize_kernel<<<(N + 255) / 256, 256, 0, S_(stream)>>>(part, n_part, N, out, out_dtype, accumulate);
+    return dle_colsum_finalize_batched(part, 1, n_part, N, out, out_dtype, accumulate, stream);
+}
+extern "C" int dle_colsum_finalize_batched(const float* part, int32_t n_arrays, int32_t n_part, int32_t N, void* out,
+                                           int32_t out_dtype, int32_t accumulate, void* stream) {
+    DLE_CHECK_ARG(part && out && n_arrays > 0 && n_part > 0 && N > 0 && (out_dtype == DLE_DTYPE_F32 || out_dtype == DLE_DTYPE_BF16));
+    colsum_finalize_kernel<<<dim3((N + 31) / 32, n_arrays), CF_WARPS * 32, 0, S_(stream)>>>(part, n_part, N, out, out_dtype, accumulate);
     DLE_LAUNCH_CHECK();
     return DLE_OK;
 }

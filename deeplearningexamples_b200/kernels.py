@@ -136,12 +136,11 @@ def add_ln_bwd(dy, z, mean, rstd, gamma, *, dropout_p=0.0, seed=0, dropout_strea
     L.launch_count["n"] += 1; L.check(lib.dle_add_ln_bwd(_ptr(dy), _ptr(z), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dz), _ptr(dx), _ptr(parts[0]),
                                _ptr(parts[1]), _ptr(parts[2]) if want_dbias else None, T, H, dropout_p, seed,
                                dropout_stream, _stream()), "dle_add_ln_bwd")
-    outs = []
-    for k in range(3 if want_dbias else 2):
-        o = torch.empty(H, device=dy.device, dtype=torch.float32)
-        L.launch_count["n"] += 1; L.check(lib.dle_colsum_finalize(_ptr(parts[k]), n_part, H, _ptr(o), L.DLE_DTYPE_F32, 0, _stream()), "dle_colsum_finalize")
-        outs.append(o)
-    return (dz, dx if dx is not None else dz, *outs)
+    na = 3 if want_dbias else 2
+    red = torch.empty((na, H), device=dy.device, dtype=torch.float32)
+    L.launch_count["n"] += 1; L.check(lib.dle_colsum_finalize_batched(_ptr(parts), na, n_part, H, _ptr(red), L.DLE_DTYPE_F32, 0, _stream()),
+                                      "dle_colsum_finalize_batched")
+    return (dz, dx if dx is not None else dz, *red.unbind(0))
 
 
 def colsum(x):
@@ -208,12 +207,10 @@ def embed_ln_bwd(dy, z, mean, rstd, gamma, input_ids, token_type_ids, V, P, NT, 
     L.launch_count["n"] += 1; L.check(lib.dle_embed_ln_bwd(_ptr(dy), _ptr(z), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(input_ids), _ptr(token_type_ids),
                                  _ptr(dword), _ptr(dpos), _ptr(dtyp), _ptr(parts[0]), _ptr(parts[1]), B, S, H, dropout_p, seed,
                                  dropout_stream, _stream()), "dle_embed_ln_bwd")
-    outs = []
-    for k in range(2):
-        o = torch.empty(H, device=dy.device, dtype=torch.float32)
-        L.launch_count["n"] += 1; L.check(lib.dle_colsum_finalize(_ptr(parts[k]), n_part, H, _ptr(o), L.DLE_DTYPE_F32, 0, _stream()), "dle_colsum_finalize")
-        outs.append(o)
-    return dword, dpos, dtyp, outs[0], outs[1]
+    red = torch.empty((2, H), device=dy.device, dtype=torch.float32)
+    L.launch_count["n"] += 1; L.check(lib.dle_colsum_finalize_batched(_ptr(parts), 2, n_part, H, _ptr(red), L.DLE_DTYPE_F32, 0, _stream()),
+                                      "dle_colsum_finalize_batched")
+    return dword, dpos, dtyp, red[0], red[1]
 
 
 def gather_rows(x, idx, err_flag=None):

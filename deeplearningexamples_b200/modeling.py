@@ -349,7 +349,29 @@ class BertLayer(nn.Module):
         else:
             self.distill_config = {'use_hidden_states': False}
 
+    def _fusable(self):
+        att = self.attention.self
+        return (not self.distillation and not att.distillation and att.attention_head_size == 64
+                and self.intermediate.dense_act.act == "gelu" and self.intermediate.dense_act.bias is not None
+                and not getattr(self, "force_modular", False))
+
     def forward(self, hidden_states, attention_mask):
+        """hidden_states (seq, bsz, hidden) -> (seq, bsz, hidden).  Default: one hand-differentiated autograd node for
+        the whole layer (ops.BertLayerFn); the module-by-module composition below computes the same function."""
+        if self._fusable():
+            att, so, it, out = self.attention.self, self.attention.output, self.intermediate.dense_act, self.output
+            S, B, H = hidden_states.shape
+            x2, restore, transposed = _tokens(hidden_states)
+            mask = None if attention_mask is None else attention_mask.reshape(B, S).to(torch.float32).contiguous()
+            w_qkv, b_qkv = att._packed()
+            tr = self.training
+            cfg = (B, S, att.num_attention_heads, att.dropout.p if tr else 0.0, so.dropout.p if tr else 0.0, so.LayerNorm.eps,
+                   att._stream_id, so._stream_id, out._stream_id, not transposed)
+            y = ops.BertLayerFn.apply(x2, mask, att.query.weight, att.key.weight, att.value.weight, att.query.bias, att.key.bias,
+                                      att.value.bias, so.dense.weight, so.dense.bias, so.LayerNorm.weight, so.LayerNorm.bias,
+                                      it.weight, it.bias, out.dense.weight, out.dense.bias, out.LayerNorm.weight, out.LayerNorm.bias,
+                                      w_qkv, b_qkv, cfg)
+            return restore(y)
         attention_output = self.attention(hidden_states, attention_mask)
         intermediate_output = self.intermediate(attention_output)
         layer_output = self.output(intermediate_output, attention_output)

@@ -193,6 +193,65 @@ class SelfAttentionFn(torch.autograd.Function):
 
 
 # -------------------------------------------------------------------------------------------------
+# whole encoder layer, hand-differentiated end to end (the default path of modeling.BertLayer)
+#   replaces BertLayer.forward (modeling.py:453-462) = BertAttention :407-410 + BertIntermediate :418-420 + BertOutput :430-434
+# Compared with composing the per-module Functions above, backward folds two more pointwise passes into GEMM
+# epilogues: gelu'(u) into the FFN2 dgrad (DLE_EPI_DGELU) and the residual-branch gradient adds into the FFN1 and
+# QKV dgrads (DLE_EPI_ADD), and hands autograd one node per layer instead of five.
+# -------------------------------------------------------------------------------------------------
+class BertLayerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mask, wq, wk, wv, bq, bk, bv, wo, bo, g1, be1, w1, b1, w2, b2, g2, be2, w_qkv, b_qkv, cfg):
+        B, S, A, p_attn, p_hid, eps, sid_attn, sid_h1, sid_h2, seq_first = cfg
+        seed_a = next_seed() if p_attn > 0.0 else 0
+        seed_1 = next_seed() if p_hid > 0.0 else 0
+        seed_2 = next_seed() if p_hid > 0.0 else 0
+        qkv = K.gemm(x, w16(w_qkv, key=wq), bias=w16(b_qkv, key=bq))
+        att, lse = K.attn_fwd(qkv, mask, B, S, A, dropout_p=p_attn, seed=seed_a, dropout_stream=sid_attn, seq_first=seq_first)
+        z1 = K.gemm(att, w16(wo), bias=w16(bo), aux=x, epilogue=L.EPI_BIAS_DROPOUT_RESIDUAL, dropout_p=p_hid, seed=seed_1,
+                    dropout_stream=sid_h1)
+        y1, _, mean1, rstd1 = K.add_ln_fwd(z1, w16(g1), w16(be1), eps=eps)
+        g, u = K.gemm(y1, w16(w1), bias=w16(b1), epilogue=L.EPI_BIAS_GELU)
+        z2 = K.gemm(g, w16(w2), bias=w16(b2), aux=y1, epilogue=L.EPI_BIAS_DROPOUT_RESIDUAL, dropout_p=p_hid, seed=seed_2,
+                    dropout_stream=sid_h2)
+        y2, _, mean2, rstd2 = K.add_ln_fwd(z2, w16(g2), w16(be2), eps=eps)
+        ctx.save_for_backward(x, mask, qkv, att, lse, z1, mean1, rstd1, y1, u, g, z2, mean2, rstd2, w_qkv)
+        ctx.params = (wq, bq, wo, bo, g1, be1, w1, b1, w2, b2, g2, be2)
+        ctx.cfg = cfg
+        ctx.seeds = (seed_a, seed_1, seed_2)
+        return y2
+
+    @staticmethod
+    def backward(ctx, dy2):
+        x, mask, qkv, att, lse, z1, mean1, rstd1, y1, u, g, z2, mean2, rstd2, w_qkv = ctx.saved_tensors
+        wq, bq, wo, bo, g1, be1, w1, b1, w2, b2, g2, be2 = ctx.params
+        B, S, A, p_attn, p_hid, eps, sid_attn, sid_h1, sid_h2, seq_first = ctx.cfg
+        seed_a, seed_1, seed_2 = ctx.seeds
+        # ---- BertOutput
+        dz2, dh2, dg2, dbe2, db2 = K.add_ln_bwd(dy2.contiguous(), z2, mean2, rstd2, w16(g2), dropout_p=p_hid, seed=seed_2,
+                                                dropout_stream=sid_h2)
+        du = K.gemm(dh2, w16(w2), b_layout=L.LAYOUT_MN, epilogue=L.EPI_DGELU, aux=u)          # dgrad * gelu'(u)
+        dw2 = wgrad(dh2, g, w2.dtype)
+        # ---- BertIntermediate (+ residual branch of BertOutput folded into the epilogue)
+        dy1 = K.gemm(du, w16(w1), b_layout=L.LAYOUT_MN, epilogue=L.EPI_ADD, aux=dz2)
+        dw1 = wgrad(du, y1, w1.dtype)
+        db1 = _to_param_dtype(K.colsum(du), b1)
+        # ---- BertSelfOutput
+        dz1, dh1, dg1, dbe1, dbo = K.add_ln_bwd(dy1, z1, mean1, rstd1, w16(g1), dropout_p=p_hid, seed=seed_1, dropout_stream=sid_h1)
+        datt = K.gemm(dh1, w16(wo), b_layout=L.LAYOUT_MN)
+        dwo = wgrad(dh1, att, wo.dtype)
+        # ---- BertSelfAttention (+ residual branch of BertSelfOutput folded into the QKV dgrad epilogue)
+        dqkv = K.attn_bwd(qkv, mask, att, datt, lse, B, S, A, dropout_p=p_attn, seed=seed_a, dropout_stream=sid_attn, seq_first=seq_first)
+        dx = K.gemm(dqkv, w16(w_qkv, key=wq), b_layout=L.LAYOUT_MN, epilogue=L.EPI_ADD, aux=dz1)
+        dwqkv = wgrad(dqkv, x, wq.dtype)
+        dbqkv = _to_param_dtype(K.colsum(dqkv), bq)
+        H = dwqkv.shape[1]
+        c = _to_param_dtype
+        return (dx, None, dwqkv[0:H], dwqkv[H:2 * H], dwqkv[2 * H:3 * H], dbqkv[0:H], dbqkv[H:2 * H], dbqkv[2 * H:3 * H],
+                dwo, c(dbo, bo), c(dg1, g1), c(dbe1, be1), dw1, db1, dw2, c(db2, b2), c(dg2, g2), c(dbe2, be2), None, None, None)
+
+
+# -------------------------------------------------------------------------------------------------
 # embeddings: dropout(LayerNorm(word[ids] + pos[arange(S)] + type[tt]))
 # replaces BertEmbeddings.forward (modeling.py:285-301)
 # -------------------------------------------------------------------------------------------------

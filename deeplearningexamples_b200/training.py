@@ -121,3 +121,25 @@ def take_optimizer_step(lr_scheduler, optimizer, grad_scaler):
     grad_scaler.step(optimizer)
     grad_scaler.update()
     optimizer.zero_grad(set_to_none=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# multi-GPU host logic (one process per GPU, pure data parallelism: run_pretraining.py:338,455-475,544-547)
+# ------------------------------------------------------------------------------------------------------------------
+def rank_seed(base_seed, rank):
+    """Each rank draws its own micro-batches: seed + rank (run_pretraining.py:544-547 seeds with seed + local_rank)."""
+    return int(base_seed) + int(rank)
+
+
+def max_over_ranks(value_ms, device="cpu"):
+    """A multi-GPU step takes as long as its slowest rank: MAX-reduce the device-timed milliseconds."""
+    import torch.distributed as dist
+    t = torch.tensor([float(value_ms)], device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item()
+
+
+def global_throughput(micro_batch, world, steps, ms_total):
+    """training_sequences_per_second exactly as the reference computes it (run_pretraining.py:748)."""
+    return micro_batch * world * steps / (ms_total / 1000.0)

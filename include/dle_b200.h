@@ -122,6 +122,9 @@ int dle_add_ln_bwd(const void* dy, const void* z, const float* mean, const float
 /* out[n] = sum_p part[p, n]; out dtype DLE_DTYPE_BF16 or DLE_DTYPE_F32; accumulate != 0 adds to out */
 int dle_colsum_finalize(const float* part, int32_t n_part, int32_t N, void* out, int32_t out_dtype,
                         int32_t accumulate, void* stream);
+/* n_arrays stacked partial sets part[a][p][n] -> out[a][n] in ONE launch (dgamma, dbeta, dbias of a LayerNorm) */
+int dle_colsum_finalize_batched(const float* part, int32_t n_arrays, int32_t n_part, int32_t N, void* out,
+                                int32_t out_dtype, int32_t accumulate, void* stream);
 /* column sum of a bf16 matrix [T, N] (bias gradients): part = fp32 [dle_colsum_partials(T), N] */
 int dle_colsum_partials(int64_t T);
 int dle_colsum_bf16(const void* x, int64_t T, int32_t N, int64_t ldx, float* part, void* stream);
