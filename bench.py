@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seq", type=int, default=512, help="512 = phase 2 (headline), 128 = phase 1")
-    ap.add_argument("--batch", type=int, default=0, help="per-GPU micro-batch (0 = 32 @512, 128 @128)")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU micro-batch (0 = 64 @512, 256 @128: SURVEY.md 8d ranges)")
     ap.add_argument("--max-pred", type=int, default=0)
     ap.add_argument("--no-dropout", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -162,7 +162,7 @@ def cpu_reference_run(cfg, S, P, ref_batch, steps, warmup):
 def workload(args):
     from deeplearningexamples_b200 import training as T
     S = args.seq
-    B = args.batch or (32 if S >= 384 else 128)
+    B = args.batch or (64 if S >= 384 else 256)
     P = args.max_pred or (80 if S >= 384 else 20)
     cfg = dict(T.BERT_LARGE)
     cfg["vocab_size"] = 30528                     # 30522 padded to a multiple of 8 (run_pretraining.py:383-384)

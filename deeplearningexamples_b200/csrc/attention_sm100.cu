@@ -43,10 +43,16 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 }
 
 // =================================================================================================
-// forward
+// forward  (v2: sized for TWO co-resident CTAs per SM so one CTA's softmax overlaps the other's MMAs)
+//   smem  : Q 16 KB + K ring 2x16 KB + V ring 2x16 KB + P 32 KB = 112 KB (+ barriers)      -> 2 CTAs in 228 KB
+//   TMEM  : S 128 cols + O 64 cols -> 256-column allocation                                -> 2 CTAs in 512 cols
+//   warps : 0 = TMA producer (+TMEM alloc), 1 = MMA issuer, 2..5 = softmax, ONE THREAD PER QUERY ROW
+//           (row max / sum are thread-local: no cross-warp exchange, no named barrier)
 // =================================================================================================
-constexpr int FWD_THREADS = 320;       // warp 0: TMA + TMEM alloc, warp 1: MMA, warps 2..9: softmax
-constexpr int FWD_SOFTMAX_THREADS = 256;
+constexpr int FWD_THREADS = 192;
+constexpr int FWD_SOFTMAX_THREADS = 128;
+constexpr int FWD_TMEM_COLS = 256;
+constexpr int FWD_SMEM_BYTES = TILE_BYTES /*Q*/ + 4 * TILE_BYTES /*K,V rings*/ + PT_BYTES /*P*/ + 256 /*barriers*/;
 
 struct AttnFwdParams {
     const float* mask;     // [B,S] additive or null
@@ -58,143 +64,177 @@ struct AttnFwdParams {
     uint32_t drop_thresh; float drop_scale; uint32_t drop_stream; unsigned long long seed;
 };
 
-__host__ __device__ inline int fwd_smem_bytes(int S) {
-    return 1024 + TILE_BYTES /*Q*/ + 2 * S * 128 /*K,V*/ + 2 * PT_BYTES /*P*/ + S * 4 /*mask*/ + 4 * TQ * 4 /*row exch*/ + 256;
-}
-
-__global__ void __launch_bounds__(FWD_THREADS, 1)
+__global__ void __launch_bounds__(FWD_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem[];
     const int S = p.S, n_chunks = S / TQ;
     uint8_t* sQ = smem;
-    uint8_t* sK = sQ + TILE_BYTES;
-    uint8_t* sV = sK + S * 128;
-    uint8_t* sP = sV + S * 128;
-    float* sMask = reinterpret_cast<float*>(sP + 2 * PT_BYTES);
-    float* sExch = sMask + S;                       // [2 parity][2 half][128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sExch + 4 * TQ);
-    uint64_t* q_full = bars;            // 1
-    uint64_t* k_full = bars + 1;        // 4
-    uint64_t* v_full = bars + 5;        // 4
-    uint64_t* s_full = bars + 9;        // 2
-    uint64_t* p_full = bars + 11;       // 2 (count 256)
-    uint64_t* pv_done = bars + 13;      // 2
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
+    uint8_t* sK = sQ + TILE_BYTES;               // [2]
+    uint8_t* sV = sK + 2 * TILE_BYTES;           // [2]
+    uint8_t* sP = sV + 2 * TILE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + PT_BYTES);
+    uint64_t* q_full = bars;             // 1
+    uint64_t* k_full = bars + 1;         // [2]
+    uint64_t* k_empty = bars + 3;        // [2]
+    uint64_t* v_full = bars + 5;         // [2]
+    uint64_t* v_empty = bars + 7;        // [2]
+    uint64_t* s_full = bars + 9;         // 1
+    uint64_t* p_full = bars + 10;        // 1 (count 128)
+    uint64_t* pv_done = bars + 11;       // 1
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
 
     if (threadIdx.x == 0) {
+        if ((smem_u32(smem) & 1023u) != 0) __trap();          // SWIZZLE_128B tiles need a 1024-byte aligned base
         tma_prefetch_desc(&tmap_qkv);
         mbar_init(q_full, 1);
-        for (int i = 0; i < 4; ++i) { mbar_init(&k_full[i], 1); mbar_init(&v_full[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], FWD_SOFTMAX_THREADS); mbar_init(&pv_done[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+        mbar_init(s_full, 1); mbar_init(p_full, FWD_SOFTMAX_THREADS / 32); mbar_init(pv_done, 1);
         fence_barrier_init();
     }
-    if (warp == 0) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
+    if (warp == 0) { tmem_alloc(tmem_ptr, FWD_TMEM_COLS); tmem_relinquish(); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 256;
+    const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + TQ;
 
     if (warp == 0) {
+        // ===================== TMA producer =====================
         if (lane == 0) {
             mbar_expect_tx(q_full, TILE_BYTES);
             tma_load_3d(sQ, &tmap_qkv, q_full, h * HD, qt * TQ, b);
             for (int j = 0; j < n_chunks; ++j) {
-                mbar_expect_tx(&k_full[j], TILE_BYTES);
-                tma_load_3d(sK + j * TILE_BYTES, &tmap_qkv, &k_full[j], p.H + h * HD, j * TQ, b);
-            }
-            for (int j = 0; j < n_chunks; ++j) {
-                mbar_expect_tx(&v_full[j], TILE_BYTES);
-                tma_load_3d(sV + j * TILE_BYTES, &tmap_qkv, &v_full[j], 2 * p.H + h * HD, j * TQ, b);
+                const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
+                mbar_wait(&k_empty[st], ph ^ 1);
+                mbar_expect_tx(&k_full[st], TILE_BYTES);
+                tma_load_3d(sK + st * TILE_BYTES, &tmap_qkv, &k_full[st], p.H + h * HD, j * TQ, b);
+                mbar_wait(&v_empty[st], ph ^ 1);
+                mbar_expect_tx(&v_full[st], TILE_BYTES);
+                tma_load_3d(sV + st * TILE_BYTES, &tmap_qkv, &v_full[st], 2 * p.H + h * HD, j * TQ, b);
             }
         }
     } else if (warp == 1) {
+        // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t idesc_s = make_idesc_bf16(TQ, TQ, false, false);
             constexpr uint32_t idesc_pv = make_idesc_bf16(TQ, HD, false, true);
             const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
             mbar_wait(q_full, 0);
-            for (int j = 0; j <= n_chunks; ++j) {
-                if (j < n_chunks) {
-                    // S_j = Q K_j^T -> TMEM S[j&1]  (buffer freed by p_full[(j-2)&1], waited in iteration j-1... see below)
-                    mbar_wait(&k_full[j], 0);
-                    tc_fence_after();
+            for (int j = 0; j < n_chunks; ++j) {
+                const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
+                // S_j = Q K_j^T.  The S columns are free: the softmax warps finished reading S_{j-1} before p_full(j-1),
+                // which this thread waited for before issuing PV_{j-1}.
+                mbar_wait(&k_full[st], ph);
+                tc_fence_after();
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        umma_bf16_ss(tmem_S + (j & 1) * TQ, make_smem_desc_sw128(aQ + kk * 32, 0, 1024),
-                                     make_smem_desc_sw128(aK + j * TILE_BYTES + kk * 32, 0, 1024), idesc_s, kk > 0 ? 1u : 0u);
-                    umma_commit(&s_full[j & 1]);
-                }
-                if (j >= 1) {
-                    const int c = j - 1;               // O += P_c V_c
-                    mbar_wait(&p_full[c & 1], (c >> 1) & 1);
-                    tc_fence_after();
-                    mbar_wait(&v_full[c], 0);
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16_ss(tmem_S, make_smem_desc_sw128(aQ + kk * 32, 0, 1024),
+                                 make_smem_desc_sw128(aK + st * TILE_BYTES + kk * 32, 0, 1024), idesc_s, kk > 0 ? 1u : 0u);
+                umma_commit(&k_empty[st]);
+                umma_commit(s_full);
+                // O += P_j V_j
+                mbar_wait(p_full, j & 1);
+                tc_fence_after();
+                mbar_wait(&v_full[st], ph);
 #pragma unroll
-                    for (int kk = 0; kk < 8; ++kk)
-                        umma_bf16_ss(tmem_O, make_smem_desc_sw128(aP + (c & 1) * PT_BYTES + (kk >> 2) * TILE_BYTES + (kk & 3) * 32, 0, 1024),
-                                     make_smem_desc_sw128(aV + c * TILE_BYTES + kk * 2048, TILE_BYTES, 1024), idesc_pv,
-                                     (c > 0 || kk > 0) ? 1u : 0u);
-                    umma_commit(&pv_done[c & 1]);
-                }
+                for (int kk = 0; kk < 8; ++kk)
+                    umma_bf16_ss(tmem_O, make_smem_desc_sw128(aP + (kk >> 2) * TILE_BYTES + (kk & 3) * 32, 0, 1024),
+                                 make_smem_desc_sw128(aV + st * TILE_BYTES + kk * 2048, TILE_BYTES, 1024), idesc_pv,
+                                 (j > 0 || kk > 0) ? 1u : 0u);
+                umma_commit(&v_empty[st]);
+                umma_commit(pv_done);
             }
         }
     } else {
-        // ===================== softmax warps =====================
-        const int q4 = warp & 3, hf = (warp - 2) >> 2;
-        const int r = q4 * 32 + lane;                                  // row inside the tile
+        // ===================== softmax warps: thread = query row =====================
+        const int q4 = warp & 3;
+        const int r = q4 * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
-        const int st = threadIdx.x - 64;                               // 0..255
-        for (int i = st; i < S; i += FWD_SOFTMAX_THREADS) sMask[i] = p.mask ? p.mask[(long long)b * S + i] * LOG2E : 0.f;
-        named_bar_sync(1, FWD_SOFTMAX_THREADS);
+        const uint32_t sp = smem_u32(sP);
         float m_run = -INFINITY, l_run = 0.f;
         const unsigned long long drop_row = ((unsigned long long)(b * p.A + h) * S + (qt * TQ + r)) * (unsigned long long)S;
-        for (int j = 0; j < n_chunks; ++j) {
-            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
-            tc_fence_after();
-            const uint32_t tS = tmem_S + lane_addr + (j & 1) * TQ + hf * 64;
-            const float* mk = sMask + j * TQ + hf * 64;
-            uint32_t v[32];
-            float mx = -INFINITY;
-#pragma unroll
-            for (int pc = 0; pc < 2; ++pc) {
-                tmem_ld32(tS + pc * 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaf(__uint_as_float(v[i]), p.scale_log2, mk[pc * 32 + i]));
+        const float* mrow = p.mask ? p.mask + (long long)b * S : nullptr;
+        // which 128-key chunks carry a non-zero additive mask (warp-uniform bit set; typical batches: none or the tail)
+        uint32_t chunk_masked = 0;
+        if (mrow) {
+            for (int j = 0; j < n_chunks; ++j) {
+                const float4 m4 = __ldg(reinterpret_cast<const float4*>(mrow + j * TQ) + lane);
+                if (__any_sync(0xffffffffu, m4.x != 0.f || m4.y != 0.f || m4.z != 0.f || m4.w != 0.f)) chunk_masked |= 1u << j;
             }
-            float* ex = sExch + (j & 1) * 2 * TQ;
-            ex[hf * TQ + r] = mx;
-            named_bar_sync(1, FWD_SOFTMAX_THREADS);
-            const float m_new = fmaxf(m_run, fmaxf(ex[r], ex[TQ + r]));
+        }
+        for (int j = 0; j < n_chunks; ++j) {
+            const bool masked = (chunk_masked >> j) & 1u;
+            const float* mk = mrow + j * TQ;
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            uint32_t v[2][32];
+            // ---- pass 1: row max over the 128 keys of this chunk (next TMEM piece in flight while this one is reduced)
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+            tmem_ld32(tmem_S + lane_addr, v[0]);
+#pragma unroll
+            for (int pc = 0; pc < 4; ++pc) {
+                tmem_ld_wait();
+                if (pc < 3) tmem_ld32(tmem_S + lane_addr + (pc + 1) * 32, v[(pc + 1) & 1]);
+                const uint32_t(&w)[32] = v[pc & 1];
+                if (masked) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 m4 = __ldg(reinterpret_cast<const float4*>(mk + pc * 32) + i);
+                        mx0 = fmaxf(mx0, fmaf(__uint_as_float(w[4 * i]), p.scale_log2, m4.x * LOG2E));
+                        mx1 = fmaxf(mx1, fmaf(__uint_as_float(w[4 * i + 1]), p.scale_log2, m4.y * LOG2E));
+                        mx2 = fmaxf(mx2, fmaf(__uint_as_float(w[4 * i + 2]), p.scale_log2, m4.z * LOG2E));
+                        mx3 = fmaxf(mx3, fmaf(__uint_as_float(w[4 * i + 3]), p.scale_log2, m4.w * LOG2E));
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        mx0 = fmaxf(mx0, __uint_as_float(w[i])); mx1 = fmaxf(mx1, __uint_as_float(w[i + 1]));
+                        mx2 = fmaxf(mx2, __uint_as_float(w[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(w[i + 3]));
+                    }
+                }
+            }
+            float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+            if (!masked) mx *= p.scale_log2;                          // scale > 0: max commutes with the scaling
+            const float m_new = fmaxf(m_run, mx);
             const float alpha = ex2(m_run - m_new);                    // 0 at j == 0
-            if (j >= 1) {                                              // PV_{j-1} done: O valid, P buffer (j&1) free
-                mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+            tmem_ld32(tmem_S + lane_addr, v[0]);                       // first piece of pass 2 in flight during the wait below
+            if (j >= 1) {                                              // PV_{j-1} retired: O is valid, the P buffer is free
+                mbar_wait(pv_done, (j - 1) & 1);
                 tc_fence_after();
             }
-            float rs = 0.f;
-            const uint32_t sp = smem_u32(sP) + (j & 1) * PT_BYTES;
+            // ---- pass 2: p = exp2(s - m), row sum (before dropout), dropout, bf16 -> swizzled smem
+            float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
 #pragma unroll
-            for (int pc = 0; pc < 2; ++pc) {
-                tmem_ld32(tS + pc * 32, v);
+            for (int pc = 0; pc < 4; ++pc) {
                 tmem_ld_wait();
+                if (pc < 3) tmem_ld32(tmem_S + lane_addr + (pc + 1) * 32, v[(pc + 1) & 1]);
+                const uint32_t(&w)[32] = v[pc & 1];
                 float e[32];
+                if (masked) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    e[i] = ex2(fmaf(__uint_as_float(v[i]), p.scale_log2, mk[pc * 32 + i]) - m_new);
-                    rs += e[i];
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 m4 = __ldg(reinterpret_cast<const float4*>(mk + pc * 32) + i);
+                        e[4 * i] = ex2(fmaf(__uint_as_float(w[4 * i]), p.scale_log2, m4.x * LOG2E) - m_new);
+                        e[4 * i + 1] = ex2(fmaf(__uint_as_float(w[4 * i + 1]), p.scale_log2, m4.y * LOG2E) - m_new);
+                        e[4 * i + 2] = ex2(fmaf(__uint_as_float(w[4 * i + 2]), p.scale_log2, m4.z * LOG2E) - m_new);
+                        e[4 * i + 3] = ex2(fmaf(__uint_as_float(w[4 * i + 3]), p.scale_log2, m4.w * LOG2E) - m_new);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) e[i] = ex2(fmaf(__uint_as_float(w[i]), p.scale_log2, -m_new));
                 }
-                const int col = hf * 64 + pc * 32;
-                if (p.drop_thresh != 0u) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) { rs0 += e[i]; rs1 += e[i + 1]; rs2 += e[i + 2]; rs3 += e[i + 3]; }
+                const int col = pc * 32;
+                if (p.drop_thresh != 0u) {                             // the 1/(1-p) scale is applied once, in the epilogue
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        const uint32_t keep = dropout_keep8(p.seed, p.drop_stream, (drop_row + j * TQ + col + g * 8) >> 3, p.drop_thresh);
+                        const uint32_t keep = dropout_keep8<7>(p.seed, p.drop_stream, (drop_row + j * TQ + col + g * 8) >> 3, p.drop_thresh);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) e[g * 8 + i] = ((keep >> i) & 1u) ? e[g * 8 + i] * p.drop_scale : 0.f;
+                        for (int i = 0; i < 8; ++i) e[g * 8 + i] = ((keep >> i) & 1u) ? e[g * 8 + i] : 0.f;
                     }
                 }
 #pragma unroll
@@ -202,53 +242,55 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdParam
                     st_shared_v4(sp + pt_offset(r, col + g * 8), pack_bf16(e[g * 8], e[g * 8 + 1]), pack_bf16(e[g * 8 + 2], e[g * 8 + 3]),
                                  pack_bf16(e[g * 8 + 4], e[g * 8 + 5]), pack_bf16(e[g * 8 + 6], e[g * 8 + 7]));
             }
-            if (j >= 1 && __any_sync(0xffffffffu, alpha != 1.0f)) {    // rescale my 32 columns of O
-                tmem_ld32(tmem_O + lane_addr + hf * 32, v);
+            if (j >= 1 && __any_sync(0xffffffffu, alpha != 1.0f)) {    // rescale this row of O (64 columns)
+                tmem_ld32(tmem_O + lane_addr, v[0]);
+                tmem_ld32(tmem_O + lane_addr + 32, v[1]);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-                tmem_st32(tmem_O + lane_addr + hf * 32, v);
+                for (int i = 0; i < 32; ++i) { v[0][i] = __float_as_uint(__uint_as_float(v[0][i]) * alpha); v[1][i] = __float_as_uint(__uint_as_float(v[1][i]) * alpha); }
+                tmem_st32(tmem_O + lane_addr, v[0]);
+                tmem_st32(tmem_O + lane_addr + 32, v[1]);
                 tmem_st_wait();
             }
-            l_run = l_run * alpha + rs;
+            l_run = l_run * alpha + ((rs0 + rs1) + (rs2 + rs3));
             m_run = m_new;
             tc_fence_before();
             fence_proxy_async_smem();
-            mbar_arrive(&p_full[j & 1]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);                       // one arrival per warp (count = 4)
         }
-        // ---- epilogue: O / l -> ctx, lse
-        const int last = n_chunks - 1;
-        mbar_wait(&pv_done[last & 1], (last >> 1) & 1);
+        // ---- epilogue: O * (1/(1-p)) / l -> ctx, lse
+        mbar_wait(pv_done, (n_chunks - 1) & 1);
         tc_fence_after();
-        float* ex = sExch + (n_chunks & 1) * 2 * TQ;
-        ex[hf * TQ + r] = l_run;
-        named_bar_sync(1, FWD_SOFTMAX_THREADS);
-        const float l_tot = ex[r] + ex[TQ + r];
-        const float inv_l = 1.0f / l_tot;
-        uint32_t v[32];
-        tmem_ld32(tmem_O + lane_addr + hf * 32, v);
-        tmem_ld_wait();
+        const float inv_l = p.drop_scale / l_run;
         const long long tok = (long long)b * p.tok_stride_b + (long long)(qt * TQ + r) * p.tok_stride_s;
-        bf16* o = p.ctx + tok * p.H + h * HD + hf * 32;
+        bf16* o = p.ctx + tok * p.H + h * HD;
+        {
+            uint32_t v[2][32];
+            tmem_ld32(tmem_O + lane_addr, v[0]);
+            tmem_ld32(tmem_O + lane_addr + 32, v[1]);
+            tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; i += 8)
-            st_global_v4(o + i, pack_bf16(__uint_as_float(v[i]) * inv_l, __uint_as_float(v[i + 1]) * inv_l),
-                         pack_bf16(__uint_as_float(v[i + 2]) * inv_l, __uint_as_float(v[i + 3]) * inv_l),
-                         pack_bf16(__uint_as_float(v[i + 4]) * inv_l, __uint_as_float(v[i + 5]) * inv_l),
-                         pack_bf16(__uint_as_float(v[i + 6]) * inv_l, __uint_as_float(v[i + 7]) * inv_l));
-        if (hf == 0) p.lse[((long long)b * p.A + h) * S + qt * TQ + r] = (m_run + log2f(l_tot)) * LN2;
+            for (int pc = 0; pc < 2; ++pc)
+#pragma unroll
+                for (int i = 0; i < 32; i += 8)
+                    st_global_v4(o + pc * 32 + i, pack_bf16(__uint_as_float(v[pc][i]) * inv_l, __uint_as_float(v[pc][i + 1]) * inv_l),
+                                 pack_bf16(__uint_as_float(v[pc][i + 2]) * inv_l, __uint_as_float(v[pc][i + 3]) * inv_l),
+                                 pack_bf16(__uint_as_float(v[pc][i + 4]) * inv_l, __uint_as_float(v[pc][i + 5]) * inv_l),
+                                 pack_bf16(__uint_as_float(v[pc][i + 6]) * inv_l, __uint_as_float(v[pc][i + 7]) * inv_l));
+        }
+        p.lse[((long long)b * p.A + h) * S + qt * TQ + r] = (m_run + log2f(l_run)) * LN2;
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, FWD_TMEM_COLS); }
 }
-
 
 // =================================================================================================
 // backward
 // =================================================================================================
-constexpr int BWD_THREADS = 320;       // warp 0: TMA + TMEM alloc, warp 1: MMA, warps 2..9: compute
-constexpr int BWD_COMPUTE_THREADS = 256;
+constexpr int BWD_THREADS = 576;       // warp 0: TMA + TMEM alloc, warp 1: MMA, warps 2..17: compute
+constexpr int BWD_COMPUTE_THREADS = 512;   // 4 warps per TMEM lane quarter, each owning 32 of the 128 tile columns
 
 struct AttnBwdParams {
     const float* mask; const float* lse; const float* delta;
@@ -319,9 +361,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_qkv); tma_prefetch_desc(&tmap_do);
         for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
-        mbar_init(kv_full, 1); mbar_init(kv_empty, 1); mbar_init(s_full, 1); mbar_init(p_full, BWD_COMPUTE_THREADS);
-        mbar_init(dp_full, 1); mbar_init(ds_full, BWD_COMPUTE_THREADS); mbar_init(pair_done, 1); mbar_init(dkv_full, 1);
-        mbar_init(dkv_read, BWD_COMPUTE_THREADS);
+        mbar_init(kv_full, 1); mbar_init(kv_empty, 1); mbar_init(s_full, 1); mbar_init(p_full, BWD_COMPUTE_THREADS / 32);
+        mbar_init(dp_full, 1); mbar_init(ds_full, BWD_COMPUTE_THREADS / 32); mbar_init(pair_done, 1); mbar_init(dkv_full, 1);
+        mbar_init(dkv_read, BWD_COMPUTE_THREADS / 32);
         fence_barrier_init();
     }
     if (warp == 0) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
@@ -400,7 +442,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         }
     } else {
         // ===================== compute warps =====================
-        const int q4 = warp & 3, hf = (warp - 2) >> 2;
+        const int q4 = warp & 3, qc = (warp - 2) >> 2;          // qc: which 32-column quarter of the tile
         const int r = q4 * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
         const int ct = threadIdx.x - 64;
@@ -409,58 +451,55 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         const long long bh = (long long)b * p.A + h;
         const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS);
         for (int j = 0; j < n; ++j) {
-            const float* mk = sMask + j * TQ + hf * 64;
+            const float* mk = sMask + j * TQ + qc * 32;
             for (int i = 0; i < n; ++i) {
                 const int t = j * n + i;
                 const float lse2 = p.lse[bh * S + i * TQ + r] * LOG2E;
                 const float dl = p.delta[bh * S + i * TQ + r];
-                const unsigned long long drop_row = (unsigned long long)(bh * S + (i * TQ + r)) * (unsigned long long)S + j * TQ + hf * 64;
-                uint32_t pk[32];                 // undropped P, packed bf16x2 (64 values)
-                uint32_t keep_lo = 0xffffffffu, keep_hi = 0xffffffffu;
+                const unsigned long long drop_row = (unsigned long long)(bh * S + (i * TQ + r)) * (unsigned long long)S + j * TQ + qc * 32;
+                uint32_t pk[16];                 // undropped P, packed bf16x2 (32 values)
+                uint32_t km = 0xffffffffu;       // keep-mask of my 32 columns
                 mbar_wait(s_full, t & 1);
                 tc_fence_after();
                 if (t >= 1) { mbar_wait(pair_done, (t - 1) & 1); tc_fence_after(); }   // sP / sdS no longer read by the tensor core
                 uint32_t v[32];
-#pragma unroll
-                for (int pc = 0; pc < 2; ++pc) {
-                    tmem_ld32(tmem_SP + lane_addr + hf * 64 + pc * 32, v);
+                {
+                    tmem_ld32(tmem_SP + lane_addr + qc * 32, v);
                     tmem_ld_wait();
                     float e[32];
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) e[k] = ex2(fmaf(__uint_as_float(v[k]), p.scale_log2, mk[pc * 32 + k]) - lse2);
+                    for (int k = 0; k < 32; ++k) e[k] = ex2(fmaf(__uint_as_float(v[k]), p.scale_log2, mk[k]) - lse2);
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) pk[pc * 16 + k] = pack_bf16(e[2 * k], e[2 * k + 1]);
+                    for (int k = 0; k < 16; ++k) pk[k] = pack_bf16(e[2 * k], e[2 * k + 1]);
                     if (p.drop_thresh != 0u) {
-                        uint32_t km = 0;
+                        km = 0;
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
-                            const uint32_t keep = dropout_keep8(p.seed, p.drop_stream, (drop_row + pc * 32 + g * 8) >> 3, p.drop_thresh);
+                            const uint32_t keep = dropout_keep8<7>(p.seed, p.drop_stream, (drop_row + g * 8) >> 3, p.drop_thresh);
                             km |= keep << (g * 8);
 #pragma unroll
                             for (int k = 0; k < 8; ++k) e[g * 8 + k] = ((keep >> k) & 1u) ? e[g * 8 + k] * p.drop_scale : 0.f;
                         }
-                        if (pc == 0) keep_lo = km; else keep_hi = km;
                     }
 #pragma unroll
                     for (int g = 0; g < 4; ++g)
-                        st_shared_v4(aP + pt_offset(r, hf * 64 + pc * 32 + g * 8), pack_bf16(e[g * 8], e[g * 8 + 1]), pack_bf16(e[g * 8 + 2], e[g * 8 + 3]),
+                        st_shared_v4(aP + pt_offset(r, qc * 32 + g * 8), pack_bf16(e[g * 8], e[g * 8 + 1]), pack_bf16(e[g * 8 + 2], e[g * 8 + 3]),
                                      pack_bf16(e[g * 8 + 4], e[g * 8 + 5]), pack_bf16(e[g * 8 + 6], e[g * 8 + 7]));
                 }
                 tc_fence_before();
                 fence_proxy_async_smem();
-                mbar_arrive(p_full);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full);
                 // ---- dS = P * (dP~ - delta) * scale
                 mbar_wait(dp_full, t & 1);
                 tc_fence_after();
-#pragma unroll
-                for (int pc = 0; pc < 2; ++pc) {
-                    tmem_ld32(tmem_SP + lane_addr + hf * 64 + pc * 32, v);
+                {
+                    tmem_ld32(tmem_SP + lane_addr + qc * 32, v);
                     tmem_ld_wait();
-                    const uint32_t km = pc == 0 ? keep_lo : keep_hi;
                     float e[32];
 #pragma unroll
                     for (int k = 0; k < 16; ++k) {
-                        const float2 pp = unpack_bf16(pk[pc * 16 + k]);
+                        const float2 pp = unpack_bf16(pk[k]);
                         float d0 = __uint_as_float(v[2 * k]), d1 = __uint_as_float(v[2 * k + 1]);
                         d0 = ((km >> (2 * k)) & 1u) ? d0 * p.drop_scale : 0.f;
                         d1 = ((km >> (2 * k + 1)) & 1u) ? d1 * p.drop_scale : 0.f;
@@ -469,18 +508,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
                     }
 #pragma unroll
                     for (int g = 0; g < 4; ++g)
-                        st_shared_v4(adS + pt_offset(r, hf * 64 + pc * 32 + g * 8), pack_bf16(e[g * 8], e[g * 8 + 1]), pack_bf16(e[g * 8 + 2], e[g * 8 + 3]),
+                        st_shared_v4(adS + pt_offset(r, qc * 32 + g * 8), pack_bf16(e[g * 8], e[g * 8 + 1]), pack_bf16(e[g * 8 + 2], e[g * 8 + 3]),
                                      pack_bf16(e[g * 8 + 4], e[g * 8 + 5]), pack_bf16(e[g * 8 + 6], e[g * 8 + 7]));
                 }
                 tc_fence_before();
                 fence_proxy_async_smem();
-                mbar_arrive(ds_full);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ds_full);
             }
             // ---- dV_j, dK_j complete: drain my 32 columns of each to global
             mbar_wait(dkv_full, j & 1);
             tc_fence_after();
             const long long tok = (long long)b * p.tok_stride_b + (long long)(j * TQ + r) * p.tok_stride_s;
             uint32_t v[32];
+            if (qc < 2) {                                        // 64-wide accumulators: two of the four column-warps drain them
+            const int hf = qc;
 #pragma unroll
             for (int which = 0; which < 2; ++which) {           // 0: dK (col block 1), 1: dV (col block 2)
                 tmem_ld32((which == 0 ? tmem_dK : tmem_dV) + lane_addr + hf * 32, v);
@@ -491,11 +533,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
                     st_global_v4(o + k, pack_bf16(__uint_as_float(v[k]), __uint_as_float(v[k + 1])), pack_bf16(__uint_as_float(v[k + 2]), __uint_as_float(v[k + 3])),
                                  pack_bf16(__uint_as_float(v[k + 4]), __uint_as_float(v[k + 5])), pack_bf16(__uint_as_float(v[k + 6]), __uint_as_float(v[k + 7])));
             }
+            }
             tc_fence_before();
-            mbar_arrive(dkv_read);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dkv_read);
         }
         // ---- all pairs done (dkv_full of the last j implies every MMA retired): drain dQ
-        for (int i = 0; i < n; ++i) {
+        for (int i = 0; i < n && qc < 2; ++i) {
+            const int hf = qc;
             uint32_t v[32];
             tmem_ld32(tmem_dQ + i * HD + lane_addr + hf * 32, v);
             tmem_ld_wait();
@@ -552,13 +597,13 @@ extern "C" int dle_attn_fwd(const void* qkv, const float* mask, void* ctx, float
     p.drop_thresh = dropout_p > 0.f ? dropout_thresh16(dropout_p) : 0u;
     p.drop_scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
     p.drop_stream = dropout_stream; p.seed = seed;
-    const int smem = fwd_smem_bytes(S);
-    static int attr_smem = 0;
-    if (smem > attr_smem) {
-        if (cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return DLE_ERR_CUDA;
-        attr_smem = smem;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM_BYTES) != cudaSuccess) return DLE_ERR_CUDA;
+        cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        attr_set = true;
     }
-    attn_fwd_kernel<<<dim3(S / TQ, A, B), FWD_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tm, p);
+    attn_fwd_kernel<<<dim3(S / TQ, A, B), FWD_THREADS, FWD_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(tm, p);
     DLE_LAUNCH_CHECK();
     return DLE_OK;
 }

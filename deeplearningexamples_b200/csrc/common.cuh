@@ -76,10 +76,11 @@ __device__ __forceinline__ float gelu_tanh_grad(float x) {
 // from (seed, stream, element-group index) with no mask tensor in HBM.
 // One call -> 128 random bits -> eight 16-bit lanes -> keep decisions for 8 consecutive elements.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+template <int ROUNDS>
+__device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < ROUNDS; ++r) {
         uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
         uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
         ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
@@ -88,8 +89,11 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
     return ctr;
 }
 // keep-mask (bit i set = keep element i of the 8-element group `group`), P(drop) = thresh16/65536.
+// ROUNDS = 10 (standard) for the [T,H] hidden dropouts; 7 (the Crush-resistant minimum of Salmon et al.) for the
+// S^2-sized attention dropout where the generator is a visible share of the softmax instruction stream.
+template <int ROUNDS = 10>
 __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint32_t stream, uint64_t group, uint32_t thresh16) {
-    uint4 r = philox4x32_10(make_uint4((uint32_t)group, (uint32_t)(group >> 32), stream, 0x5eedu),
+    uint4 r = philox4x32<ROUNDS>(make_uint4((uint32_t)group, (uint32_t)(group >> 32), stream, 0x5eedu),
                             make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
     uint32_t m = 0;
     m |= ((r.x & 0xffffu) >= thresh16) << 0; m |= ((r.x >> 16) >= thresh16) << 1;

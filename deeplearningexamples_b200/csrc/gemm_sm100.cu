@@ -190,7 +190,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], GEMM_EPI_THREADS); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], GEMM_EPI_THREADS / 32); }
         fence_barrier_init();
     }
     if (warp == 2) { tmem_alloc(tmem_ptr, Cfg::TMEM_COLS); tmem_relinquish(); }
@@ -288,7 +288,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 if (row < p.M) epilogue_strip(p, r, row, n_blk * BN + c * 32);
             }
             tc_fence_before();
-            mbar_arrive(&tmem_empty[acc]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);    // one arrival per epilogue warp
         }
     }
 

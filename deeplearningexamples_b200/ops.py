@@ -18,12 +18,16 @@ bf16 = torch.bfloat16
 # RNG bookkeeping for dropout: one 64-bit seed per forward call site, drawn from a host counter.
 # -------------------------------------------------------------------------------------------------
 _rng = {"base": None, "counter": 0}
+_stream_ids = {"next": 1}
 _MASK64 = (1 << 64) - 1
 
 
 def manual_seed(seed):
+    """Reset the dropout RNG: base seed, per-call counter and the call-site stream-id allocator (so that a model built
+    and run after manual_seed(s) reproduces its masks exactly)."""
     _rng["base"] = int(seed) & _MASK64
     _rng["counter"] = 0
+    _stream_ids["next"] = 1
 
 
 def next_seed():
@@ -31,9 +35,6 @@ def next_seed():
         _rng["base"] = torch.initial_seed() & _MASK64
     _rng["counter"] += 1
     return (_rng["base"] * 0x9E3779B97F4A7C15 + _rng["counter"] * 0xD1B54A32D192ED03) & _MASK64
-
-
-_stream_ids = {"next": 1}
 
 
 def new_stream_id():
