@@ -352,7 +352,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     uint64_t* ds_full = bars + 9;     // count 256
     uint64_t* pair_done = bars + 10;
     uint64_t* dkv_full = bars + 11;
-    uint64_t* dkv_read = bars + 12;   // count 256
+    uint64_t* dkv_read = bars + 12;   // one arrival per compute warp
+    uint64_t* dv_done = bars + 13;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -363,7 +364,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
         mbar_init(kv_full, 1); mbar_init(kv_empty, 1); mbar_init(s_full, 1); mbar_init(p_full, BWD_COMPUTE_THREADS / 32);
         mbar_init(dp_full, 1); mbar_init(ds_full, BWD_COMPUTE_THREADS / 32); mbar_init(pair_done, 1); mbar_init(dkv_full, 1);
-        mbar_init(dkv_read, BWD_COMPUTE_THREADS / 32);
+        mbar_init(dkv_read, BWD_COMPUTE_THREADS / 32); mbar_init(dv_done, 1);
         fence_barrier_init();
     }
     if (warp == 0) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
@@ -395,22 +396,28 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             constexpr uint32_t id_mm = make_idesc_bf16(TQ, HD, true, true);       // dV, dK
             constexpr uint32_t id_km = make_idesc_bf16(TQ, HD, false, true);      // dQ
             const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP), adS = smem_u32(sdS);
+            // Issue order (per pair t = j*n + i) is chosen so that the compute warps never wait behind MMAs they do not need:
+            //   ... ds_full(t-1) -> [S(t)] -> dK(t-1), dQ(t-1) | p_full(t) -> dP(t) -> dV(t) | ds_full(t) -> [S(t+1)] -> dK(t), dQ(t) ...
+            // S(t+1) goes first after ds_full(t) (its TMEM columns are free once dP(t) was consumed), so P(t+1) is computed
+            // while dK(t)/dQ(t) execute; dP(t) goes before dV(t) so dS(t) is computed while dV(t) executes.
+            auto issue_s = [&](int t_, uint32_t aQ_) {
+                mbar_wait(&qdo_full[t_ & 1], (t_ >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16_ss(tmem_SP, make_smem_desc_sw128(aQ_ + kk * 32, 0, 1024), make_smem_desc_sw128(aK + kk * 32, 0, 1024),
+                                 id_kk, kk > 0 ? 1u : 0u);
+                umma_commit(s_full);
+            };
             for (int j = 0; j < n; ++j) {
                 mbar_wait(kv_full, j & 1);
                 if (j >= 1) mbar_wait(dkv_read, (j - 1) & 1);       // dV/dK accumulators drained
                 tc_fence_after();
+                issue_s(j * n, smem_u32(sQ) + ((j * n) & 1) * TILE_BYTES);      // first pair of this kv tile
                 for (int i = 0; i < n; ++i) {
                     const int t = j * n + i, st = t & 1;
                     const uint32_t aQ = smem_u32(sQ) + st * TILE_BYTES, adO = smem_u32(sdO) + st * TILE_BYTES;
-                    mbar_wait(&qdo_full[st], (t >> 1) & 1);
-                    tc_fence_after();
-                    // (1) S = Q_i K_j^T
-#pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        umma_bf16_ss(tmem_SP, make_smem_desc_sw128(aQ + kk * 32, 0, 1024), make_smem_desc_sw128(aK + kk * 32, 0, 1024),
-                                     id_kk, kk > 0 ? 1u : 0u);
-                    umma_commit(s_full);
-                    // (2) dP = dO_i V_j^T (overwrites S once the compute warps have consumed it) ; dV_j += P~^T dO_i
+                    // dP = dO_i V_j^T (overwrites S once the compute warps have consumed it), then dV_j += P~^T dO_i
                     mbar_wait(p_full, t & 1);
                     tc_fence_after();
 #pragma unroll
@@ -422,9 +429,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
                     for (int kk = 0; kk < 8; ++kk)
                         umma_bf16_ss(tmem_dV, make_smem_desc_sw128(aP + kk * 2048, TILE_BYTES, 1024),
                                      make_smem_desc_sw128(adO + kk * 2048, TILE_BYTES, 1024), id_mm, (i > 0 || kk > 0) ? 1u : 0u);
-                    // (3) dK_j += dS^T Q_i ; dQ_i += dS K_j
+                    umma_commit(dv_done);                            // sP may be overwritten
+                    // dS ready: next S first (same kv tile only: sK must stay), then dK_j += dS^T Q_i ; dQ_i += dS K_j
                     mbar_wait(ds_full, t & 1);
                     tc_fence_after();
+                    if (i + 1 < n) issue_s(t + 1, smem_u32(sQ) + ((t + 1) & 1) * TILE_BYTES);
 #pragma unroll
                     for (int kk = 0; kk < 8; ++kk)
                         umma_bf16_ss(tmem_dK, make_smem_desc_sw128(adS + kk * 2048, TILE_BYTES, 1024),
@@ -461,7 +470,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
                 uint32_t km = 0xffffffffu;       // keep-mask of my 32 columns
                 mbar_wait(s_full, t & 1);
                 tc_fence_after();
-                if (t >= 1) { mbar_wait(pair_done, (t - 1) & 1); tc_fence_after(); }   // sP / sdS no longer read by the tensor core
+                if (t >= 1) { mbar_wait(dv_done, (t - 1) & 1); tc_fence_after(); }     // dV(t-1) retired: sP may be overwritten
                 uint32_t v[32];
                 {
                     tmem_ld32(tmem_SP + lane_addr + qc * 32, v);
@@ -493,6 +502,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
                 // ---- dS = P * (dP~ - delta) * scale
                 mbar_wait(dp_full, t & 1);
                 tc_fence_after();
+                if (t >= 1) { mbar_wait(pair_done, (t - 1) & 1); tc_fence_after(); }   // dK/dQ(t-1) retired: sdS may be overwritten
                 {
                     tmem_ld32(tmem_SP + lane_addr + qc * 32, v);
                     tmem_ld_wait();
