@@ -72,7 +72,7 @@ __device__ __forceinline__ float gelu_tanh_grad(float x) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Philox4x32-10: counter-based RNG, so forward and backward regenerate identical dropout masks
+// Philox4x32-7: counter-based RNG, so forward and backward regenerate identical dropout masks
 // from (seed, stream, element-group index) with no mask tensor in HBM.
 // One call -> 128 random bits -> eight 16-bit lanes -> keep decisions for 8 consecutive elements.
 // ---------------------------------------------------------------------------------------------
@@ -89,9 +89,9 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
     return ctr;
 }
 // keep-mask (bit i set = keep element i of the 8-element group `group`), P(drop) = thresh16/65536.
-// ROUNDS = 10 (standard) for the [T,H] hidden dropouts; 7 (the Crush-resistant minimum of Salmon et al.) for the
-// S^2-sized attention dropout where the generator is a visible share of the softmax instruction stream.
-template <int ROUNDS = 10>
+// ROUNDS = 7 is the Crush-resistant minimum of Salmon et al. (Random123); the generator is a visible share of the
+// softmax / epilogue instruction streams, so the 3 rounds of extra safety margin of Philox-10 are not spent here.
+template <int ROUNDS = 7>
 __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint32_t stream, uint64_t group, uint32_t thresh16) {
     uint4 r = philox4x32<ROUNDS>(make_uint4((uint32_t)group, (uint32_t)(group >> 32), stream, 0x5eedu),
                             make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));

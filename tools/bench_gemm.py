@@ -51,6 +51,12 @@ def main():
         ("dgrad ffn1 dy[T,I]·W1[I,H]", lambda: k.gemm(xi, w_1, b_layout=L.LAYOUT_MN), lambda: xi @ w_1, 2 * T * H * I),
         ("dgrad qkv dy[T,3H]·W[3H,H]", lambda: k.gemm(dy3, w_qkv, b_layout=L.LAYOUT_MN), lambda: dy3 @ w_qkv, 2 * T * H * 3 * H),
     ]
+    for tn in (0, 128):
+        cases.append((f"fwd out tile_n={tn or 256}", lambda tn=tn: k.gemm(x, w_o, tile_n=tn), None, 2 * T * H * H))
+        cases.append((f"fwd out +drop+res tile_n={tn or 256}", lambda tn=tn: k.gemm(x, w_o, bias=b_i[:H], aux=x, epilogue=L.EPI_BIAS_DROPOUT_RESIDUAL, dropout_p=0.1, seed=1, tile_n=tn), None, 2 * T * H * H))
+        cases.append((f"fwd ffn2 +drop+res tile_n={tn or 256}", lambda tn=tn: k.gemm(xi, w_2, bias=b_i[:H], aux=x, epilogue=L.EPI_BIAS_DROPOUT_RESIDUAL, dropout_p=0.1, seed=1, tile_n=tn), None, 2 * T * H * I))
+        cases.append((f"dgrad ffn1 tile_n={tn or 256}", lambda tn=tn: k.gemm(xi, w_1, b_layout=L.LAYOUT_MN, tile_n=tn), None, 2 * T * H * I))
+        cases.append((f"dgrad out tile_n={tn or 256}", lambda tn=tn: k.gemm(x, w_o, b_layout=L.LAYOUT_MN, tile_n=tn), None, 2 * T * H * H))
     for splits in (1, 2, 4, 8):
         cases.append((f"wgrad ffn1 dy[T,I]^T·x[T,H] splits={splits}",
                       lambda s=splits: k.gemm(xi, x, a_layout=L.LAYOUT_MN, b_layout=L.LAYOUT_MN, epilogue=L.EPI_ATOMIC_F32, splits=s,
