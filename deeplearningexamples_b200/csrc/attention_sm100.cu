@@ -230,12 +230,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdParam
                 for (int i = 0; i < 32; i += 4) { rs0 += e[i]; rs1 += e[i + 1]; rs2 += e[i + 2]; rs3 += e[i + 3]; }
                 const int col = pc * 32;
                 if (p.drop_thresh != 0u) {                             // the 1/(1-p) scale is applied once, in the epilogue
+                    const uint32_t keep = dropout_keep32(p.seed, p.drop_stream, (drop_row + j * TQ + col) >> 5, p.drop_thresh);
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const uint32_t keep = dropout_keep8<7>(p.seed, p.drop_stream, (drop_row + j * TQ + col + g * 8) >> 3, p.drop_thresh);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) e[g * 8 + i] = ((keep >> i) & 1u) ? e[g * 8 + i] : 0.f;
-                    }
+                    for (int i = 0; i < 32; ++i) e[i] = ((keep >> i) & 1u) ? e[i] : 0.f;
                 }
 #pragma unroll
                 for (int g = 0; g < 4; ++g)
@@ -481,14 +478,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
 #pragma unroll
                     for (int k = 0; k < 16; ++k) pk[k] = pack_bf16(e[2 * k], e[2 * k + 1]);
                     if (p.drop_thresh != 0u) {
-                        km = 0;
+                        km = dropout_keep32(p.seed, p.drop_stream, drop_row >> 5, p.drop_thresh);
 #pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            const uint32_t keep = dropout_keep8<7>(p.seed, p.drop_stream, (drop_row + g * 8) >> 3, p.drop_thresh);
-                            km |= keep << (g * 8);
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) e[g * 8 + k] = ((keep >> k) & 1u) ? e[g * 8 + k] * p.drop_scale : 0.f;
-                        }
+                        for (int k = 0; k < 32; ++k) e[k] = ((km >> k) & 1u) ? e[k] * p.drop_scale : 0.f;
                     }
 #pragma unroll
                     for (int g = 0; g < 4; ++g)

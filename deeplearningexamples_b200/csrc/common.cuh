@@ -102,6 +102,29 @@ __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint32_t stream
     m |= ((r.w & 0xffffu) >= thresh16) << 6; m |= ((r.w >> 16) >= thresh16) << 7;
     return m;
 }
+// 32 keep-bits for the 32 consecutive elements of group `group32` (element index >> 5): ONE Philox4x32-7 call gives four
+// independent 32-bit words; each word seeds a 32-bit LCG (x <- x*747796405 + 2891336453, PCG's multiplier/increment) that is
+// stepped 7 times, and the top 16 bits of each state are compared with the 16-bit threshold.  The keyed, Crush-resistant
+// generator decorrelates groups; inside a group the LCG's high bits are more than adequate for Bernoulli(p) decisions.
+// Cost ~1.75 (Philox, amortised) + 3 instructions per element instead of ~10.
+template <int ROUNDS = 7>
+__device__ __forceinline__ uint32_t dropout_keep32(uint64_t seed, uint32_t stream, uint64_t group32, uint32_t thresh16) {
+    const uint4 r = philox4x32<ROUNDS>(make_uint4((uint32_t)group32, (uint32_t)(group32 >> 32), stream, 0x5eed32u),
+                                       make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint32_t t = thresh16 << 16;
+    uint32_t x[4] = {r.x, r.y, r.z, r.w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        uint32_t s = x[w];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            m |= (s >= t ? 1u : 0u) << (w * 8 + k);
+            s = s * 747796405u + 2891336453u;
+        }
+    }
+    return m;
+}
 __host__ __device__ __forceinline__ uint32_t dropout_thresh16(float p) {
     float t = p * 65536.0f + 0.5f;
     return t <= 0.f ? 0u : (t >= 65535.f ? 65535u : (uint32_t)t);

@@ -161,13 +161,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
         for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(__bfloat162float(__float2bfloat16_rn(v[i])));
     } else if (p.epilogue == DLE_EPI_BIAS_DROPOUT_RESIDUAL) {
         if (p.drop_thresh != 0) {
+            const uint32_t keep = dropout_keep32(p.seed, p.drop_stream, (unsigned long long)(row * (long long)p.N + col0) >> 5, p.drop_thresh);
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-                unsigned long long grp = (unsigned long long)(row * (long long)p.N + col0 + i) >> 3;
-                uint32_t keep = dropout_keep8(p.seed, p.drop_stream, grp, p.drop_thresh);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[i + j] = ((keep >> j) & 1u) ? v[i + j] * p.drop_scale : 0.f;
-            }
+            for (int i = 0; i < 32; ++i) v[i] = ((keep >> i) & 1u) ? v[i] * p.drop_scale : 0.f;
         }
         if (p.aux != nullptr) {
             float a[32];
@@ -428,6 +424,7 @@ extern "C" int dle_gemm_bf16(const dle_gemm_args* a, void* stream_) {
     // M and K are otherwise free (TMA zero-fills out-of-bounds rows/columns of partial tiles).
     DLE_CHECK_ARG(a->N % 8 == 0 && a->ldo % 8 == 0 && a->lda % 8 == 0 && a->ldb % 8 == 0);
     DLE_CHECK_ARG(a->epilogue >= 0 && a->epilogue < DLE_EPI_COUNT);
+    if (a->epilogue == DLE_EPI_BIAS_DROPOUT_RESIDUAL && a->dropout_p > 0.f) DLE_CHECK_ARG(a->N % 32 == 0);   // 32-element RNG groups
     if (a->epilogue == DLE_EPI_BIAS_GELU) DLE_CHECK_ARG(a->out2 != nullptr && a->ldo2 % 8 == 0);
     if (a->epilogue == DLE_EPI_DGELU || a->epilogue == DLE_EPI_ADD) DLE_CHECK_ARG(a->aux != nullptr);
     if (a->aux != nullptr) DLE_CHECK_ARG(a->ld_aux % 8 == 0);

@@ -76,7 +76,7 @@ add_ln_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ bias, con
 #pragma unroll
             for (int i = 0; i < 8; ++i) z[j * 8 + i] += bs[j * 8 + i];
             if (thresh != 0u) {
-                const uint32_t keep = dropout_keep8(seed, stream_id, (unsigned long long)(row * H + col) >> 3, thresh);
+                const uint32_t keep = ((dropout_keep32(seed, stream_id, (unsigned long long)(row * H + col) >> 5, thresh) >> (col & 31)) & 0xffu);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) z[j * 8 + i] = ((keep >> i) & 1u) ? z[j * 8 + i] * drop_scale : 0.f;
             }
@@ -155,7 +155,7 @@ add_ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, const
             for (int i = 0; i < 8; ++i) dzv[i] = rstd * (g[j * 8 + i] - s1 - xh[j * 8 + i] * s2);
             if (dz_out) *reinterpret_cast<uint4*>(dz_out + row * H + col) = pack8(dzv);
             if (thresh != 0u) {
-                const uint32_t keep = dropout_keep8(seed, stream_id, (unsigned long long)(row * H + col) >> 3, thresh);
+                const uint32_t keep = ((dropout_keep32(seed, stream_id, (unsigned long long)(row * H + col) >> 5, thresh) >> (col & 31)) & 0xffu);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) dzv[i] = ((keep >> i) & 1u) ? dzv[i] * drop_scale : 0.f;
                 if (dx_out) *reinterpret_cast<uint4*>(dx_out + row * H + col) = pack8(dzv);
@@ -332,7 +332,7 @@ embed_ln_fwd_kernel(const long long* __restrict__ ids, const long long* __restri
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[i] = (z[j * 8 + i] - mean) * rstd * gm[j * 8 + i] + bt[j * 8 + i];
             if (thresh != 0u) {
-                const uint32_t keep = dropout_keep8(seed, stream_id, (unsigned long long)(row * H + col) >> 3, thresh);
+                const uint32_t keep = ((dropout_keep32(seed, stream_id, (unsigned long long)(row * H + col) >> 5, thresh) >> (col & 31)) & 0xffu);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) o[i] = ((keep >> i) & 1u) ? o[i] * drop_scale : 0.f;
             }
@@ -369,7 +369,7 @@ embed_ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, con
             unpack8(ld_global_nc_v4(dy + row * H + col), d);
             unpack8(ld_global_nc_v4(z + row * H + col), zz);
             if (thresh != 0u) {
-                const uint32_t keep = dropout_keep8(seed, stream_id, (unsigned long long)(row * H + col) >> 3, thresh);
+                const uint32_t keep = ((dropout_keep32(seed, stream_id, (unsigned long long)(row * H + col) >> 5, thresh) >> (col & 31)) & 0xffu);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) d[i] = ((keep >> i) & 1u) ? d[i] * drop_scale : 0.f;
             }
