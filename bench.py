@@ -291,6 +291,11 @@ def run_ours(args):
     value = T.global_throughput(B, n, args.steps, ms_res)
     e2e = T.global_throughput(B, n, args.steps, ms_e2e)
     pk = peaks()
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if os.path.exists(tpath):                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj["avg_dram_traffic_bytes_per_launch"], "profiles/r01_gemm_traffic.json (ncu --set full, 12 forward GEMM launches of this command)"
     gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof)
     gemm_flops = sum(f for _, _, f, _ in prof)
     ach = gemm_flops / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
@@ -304,7 +309,9 @@ def run_ours(args):
             "roofline": {"kernel": "gemm_bf16_tcgen05_kernel (all dense projections/FFN, fwd+dgrad+wgrad)", "bound": "tensor",
                          "achieved": round(ach, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": round(ach / pk["tf_sustained"], 4),
                          "peak_source": pk["source"] + " (bf16_tflops_sustained: kernel timed inside a long step)",
-                         "traffic": None, "launches_timed": len(prof), "share_of_step": round(gemm_ms / ms_e2e, 4),
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch_avg": int(sum(2.0 * (m * k + n * k + m * n) for _, _, _, (m, n, k, *_r) in prof) / max(len(prof), 1)),
+                         "launches_timed": len(prof), "share_of_step": round(gemm_ms / ms_e2e, 4),
                          "how": "CUDA events around every GEMM launch on the launching stream during the e2e timed pass; "
                                 "algorithmic flops = 2*M*N*K per launch"},
             "model_flops_utilisation": {"train_gflop_per_seq": round(flops_seq / 1e9, 1),
