@@ -44,6 +44,7 @@ SIGNATURES = {
     "dle_attn_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _u64, _u32, _vp]),
     "dle_add_ln_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _u64, _u32, _vp]),
     "dle_ln_bwd_partials": (_i32, [_i64]),
+    "dle_ln_bwd_partials_h": (_i32, [_i64, _i32]),
     "dle_add_ln_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _u64, _u32, _vp]),
     "dle_colsum_finalize": (_i32, [_vp, _i32, _i32, _vp, _i32, _i32, _vp]),
     "dle_colsum_finalize_batched": (_i32, [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _vp]),

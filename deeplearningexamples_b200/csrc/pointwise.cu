@@ -7,6 +7,7 @@
 // LinearActivation bias+gelu :121-122,156-160, BertEmbeddings :285-301, index_select :590.
 #include "common.cuh"
 #include "../../include/dle_b200.h"
+#include <stdlib.h>
 
 namespace dle {
 
@@ -185,6 +186,176 @@ add_ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, const
             outs[k][(long long)blockIdx.x * H + c] = s;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Two-warps-per-row variants (H % 512 == 0).  The one-warp-per-row kernels above keep 3 x 32 column accumulators + 32 gammas
+// per lane (255 registers at H = 1024 => 8 resident warps per SM, ~50 % of HBM peak); with 64 lanes per row each lane owns
+// 16 columns, registers halve and occupancy doubles.  Row statistics cross the two warps through a double-buffered smem slot
+// and a 64-thread named barrier.
+// ---------------------------------------------------------------------------------------------
+constexpr int LN2_ROWS = 4;                       // row groups per CTA
+constexpr int LN2_THREADS = LN2_ROWS * 64;
+
+__device__ __forceinline__ void pair_bar(int rg) { asm volatile("bar.sync %0, 64;" ::"r"(rg + 1) : "memory"); }
+
+template <int J2>   // H = J2 * 512
+__global__ void __launch_bounds__(LN2_THREADS)
+add_ln_fwd2_kernel(const bf16* __restrict__ x, const bf16* __restrict__ bias, const bf16* __restrict__ residual,
+                   const bf16* __restrict__ gamma, const bf16* __restrict__ beta, bf16* __restrict__ z_out,
+                   bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, long long T, float eps,
+                   uint32_t thresh, float drop_scale, unsigned long long seed, uint32_t stream_id) {
+    constexpr int H = J2 * 512;
+    __shared__ float ex[2][LN2_ROWS][2][2];        // [parity][row group][warp of the pair][slot]
+    const int t64 = threadIdx.x & 63, rg = threadIdx.x >> 6, wp = (threadIdx.x >> 5) & 1, lane = threadIdx.x & 31;
+    uint4 gm[J2], bt[J2], bs[J2];
+#pragma unroll
+    for (int j = 0; j < J2; ++j) {
+        const int col = j * 512 + t64 * 8;
+        gm[j] = *reinterpret_cast<const uint4*>(gamma + col);
+        bt[j] = *reinterpret_cast<const uint4*>(beta + col);
+        bs[j] = bias ? *reinterpret_cast<const uint4*>(bias + col) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    int par = 0;
+    for (long long row = (long long)blockIdx.x * LN2_ROWS + rg; row < T; row += (long long)gridDim.x * LN2_ROWS, par ^= 1) {
+        float z[J2 * 8];
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < J2; ++j) {
+            const int col = j * 512 + t64 * 8;
+            float b[8];
+            unpack8(ld_global_nc_v4(x + row * H + col), z + j * 8);
+            unpack8(bs[j], b);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) z[j * 8 + i] += b[i];
+            if (thresh != 0u) {
+                const uint32_t keep = (dropout_keep32(seed, stream_id, (unsigned long long)(row * H + col) >> 5, thresh) >> (col & 31)) & 0xffu;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) z[j * 8 + i] = ((keep >> i) & 1u) ? z[j * 8 + i] * drop_scale : 0.f;
+            }
+            if (residual) {
+                float r[8];
+                unpack8(ld_global_nc_v4(residual + row * H + col), r);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) z[j * 8 + i] += r[i];
+            }
+            if (z_out) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) z[j * 8 + i] = round_bf16(z[j * 8 + i]);
+                *reinterpret_cast<uint4*>(z_out + row * H + col) = pack8(z + j * 8);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s += z[j * 8 + i];
+        }
+        s = warp_sum(s);
+        if (lane == 0) ex[par][rg][wp][0] = s;
+        pair_bar(rg);
+        const float mean = (ex[par][rg][0][0] + ex[par][rg][1][0]) / (float)H;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < J2 * 8; ++i) { const float d = z[i] - mean; q += d * d; }
+        q = warp_sum(q);
+        if (lane == 0) ex[par][rg][wp][1] = q;
+        pair_bar(rg);
+        const float rstd = 1.0f / sqrtf((ex[par][rg][0][1] + ex[par][rg][1][1]) / (float)H + eps);
+        if (t64 == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+#pragma unroll
+        for (int j = 0; j < J2; ++j) {
+            float g[8], b[8], o[8];
+            unpack8(gm[j], g); unpack8(bt[j], b);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = (z[j * 8 + i] - mean) * rstd * g[i] + b[i];
+            *reinterpret_cast<uint4*>(y + row * H + j * 512 + t64 * 8) = pack8(o);
+        }
+    }
+}
+
+template <int J2>
+__global__ void __launch_bounds__(LN2_THREADS)
+add_ln_bwd2_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, const float* __restrict__ mean_in,
+                   const float* __restrict__ rstd_in, const bf16* __restrict__ gamma, bf16* __restrict__ dz_out,
+                   bf16* __restrict__ dx_out, float* __restrict__ part_dgamma, float* __restrict__ part_dbeta,
+                   float* __restrict__ part_dbias, long long T, uint32_t thresh, float drop_scale,
+                   unsigned long long seed, uint32_t stream_id) {
+    constexpr int H = J2 * 512;
+    __shared__ float ex[2][LN2_ROWS][2][2];
+    __shared__ float red[LN2_ROWS][H];
+    const int t64 = threadIdx.x & 63, rg = threadIdx.x >> 6, wp = (threadIdx.x >> 5) & 1, lane = threadIdx.x & 31;
+    uint4 gm[J2];
+    float ag[J2 * 8], ab[J2 * 8], ax[J2 * 8];
+#pragma unroll
+    for (int j = 0; j < J2; ++j) gm[j] = *reinterpret_cast<const uint4*>(gamma + j * 512 + t64 * 8);
+#pragma unroll
+    for (int i = 0; i < J2 * 8; ++i) { ag[i] = 0.f; ab[i] = 0.f; ax[i] = 0.f; }
+    const float invH = 1.0f / (float)H;
+    int par = 0;
+    for (long long row = (long long)blockIdx.x * LN2_ROWS + rg; row < T; row += (long long)gridDim.x * LN2_ROWS, par ^= 1) {
+        const float mean = mean_in[row], rstd = rstd_in[row];
+        float g[J2 * 8], xh[J2 * 8];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < J2; ++j) {
+            const int col = j * 512 + t64 * 8;
+            float d[8], zz[8], gg[8];
+            unpack8(ld_global_nc_v4(dy + row * H + col), d);
+            unpack8(ld_global_nc_v4(z + row * H + col), zz);
+            unpack8(gm[j], gg);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float xhat = (zz[i] - mean) * rstd;
+                xh[j * 8 + i] = xhat;
+                ag[j * 8 + i] += d[i] * xhat;
+                ab[j * 8 + i] += d[i];
+                const float t = d[i] * gg[i];
+                g[j * 8 + i] = t;
+                s1 += t; s2 += t * xhat;
+            }
+        }
+        s1 = warp_sum(s1); s2 = warp_sum(s2);
+        if (lane == 0) { ex[par][rg][wp][0] = s1; ex[par][rg][wp][1] = s2; }
+        pair_bar(rg);
+        s1 = (ex[par][rg][0][0] + ex[par][rg][1][0]) * invH;
+        s2 = (ex[par][rg][0][1] + ex[par][rg][1][1]) * invH;
+#pragma unroll
+        for (int j = 0; j < J2; ++j) {
+            const int col = j * 512 + t64 * 8;
+            float dzv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dzv[i] = rstd * (g[j * 8 + i] - s1 - xh[j * 8 + i] * s2);
+            if (dz_out) *reinterpret_cast<uint4*>(dz_out + row * H + col) = pack8(dzv);
+            if (thresh != 0u) {
+                const uint32_t keep = (dropout_keep32(seed, stream_id, (unsigned long long)(row * H + col) >> 5, thresh) >> (col & 31)) & 0xffu;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dzv[i] = ((keep >> i) & 1u) ? dzv[i] * drop_scale : 0.f;
+                if (dx_out) *reinterpret_cast<uint4*>(dx_out + row * H + col) = pack8(dzv);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ax[j * 8 + i] += round_bf16(dzv[i]);
+        }
+    }
+    float* outs[3] = {part_dgamma, part_dbeta, part_dbias};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (outs[k] == nullptr) continue;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < J2; ++j)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) red[rg][j * 512 + t64 * 8 + i] = (k == 0) ? ag[j * 8 + i] : (k == 1 ? ab[j * 8 + i] : ax[j * 8 + i]);
+        __syncthreads();
+        for (int c = threadIdx.x; c < H; c += LN2_THREADS) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < LN2_ROWS; ++w) t += red[w][c];
+            outs[k][(long long)blockIdx.x * H + c] = t;
+        }
+    }
+}
+// DLE_LN_ONE_WARP=1 selects the one-warp-per-row kernels (A/B measurements)
+static bool ln_force_one_warp() { const char* e = getenv("DLE_LN_ONE_WARP"); return e && e[0] == '1'; }
+static int ln2_grid(long long T) {
+    long long g = (T + LN2_ROWS - 1) / LN2_ROWS, cap = (long long)sm_count() * 4;
+    return (int)(g < cap ? (g > 0 ? g : 1) : cap);
 }
 
 // out[a][n] = sum_p part[a][p][n]   (grid: (ceil(N/32), n_arrays); 16 warps stride over the partial rows, each
@@ -493,13 +664,22 @@ extern "C" int dle_add_ln_fwd(const void* x, const void* bias, const void* resid
     if (bias || residual || dropout_p > 0.f) DLE_CHECK_ARG(z_out != nullptr);
     const uint32_t th = dropout_p > 0.f ? dropout_thresh16(dropout_p) : 0u;
     const float sc = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
+    if (H % 512 == 0 && !ln_force_one_warp()) {
+        if (H == 1024) add_ln_fwd2_kernel<2><<<ln2_grid(T), LN2_THREADS, 0, S_(stream)>>>(B_(x), B_(bias), B_(residual), B_(gamma), B_(beta), BM_(z_out), BM_(y), mean, rstd, T, eps, th, sc, seed, dropout_stream);
+        else add_ln_fwd2_kernel<1><<<ln2_grid(T), LN2_THREADS, 0, S_(stream)>>>(B_(x), B_(bias), B_(residual), B_(gamma), B_(beta), BM_(z_out), BM_(y), mean, rstd, T, eps, th, sc, seed, dropout_stream);
+        DLE_LAUNCH_CHECK();
+        return DLE_OK;
+    }
     LN_DISPATCH(H, (add_ln_fwd_kernel<J><<<ln_grid(T), LN_THREADS, 0, S_(stream)>>>(B_(x), B_(bias), B_(residual), B_(gamma), B_(beta),
                     BM_(z_out), BM_(y), mean, rstd, T, eps, th, sc, seed, dropout_stream)));
     DLE_LAUNCH_CHECK();
     return DLE_OK;
 }
 
-extern "C" int dle_ln_bwd_partials(int64_t T) { return ln_grid(T); }
+// upper bound valid for both kernel families (the caller sizes the partial workspace with it; rows beyond the launched grid
+// are simply not written and dle_colsum_finalize is given the actual count through dle_ln_bwd_partials_h)
+extern "C" int dle_ln_bwd_partials(int64_t T) { int a = ln_grid(T), b = ln2_grid(T); return a > b ? a : b; }
+extern "C" int dle_ln_bwd_partials_h(int64_t T, int32_t H) { return (H % 512 == 0 && !ln_force_one_warp()) ? ln2_grid(T) : ln_grid(T); }
 
 extern "C" int dle_add_ln_bwd(const void* dy, const void* z, const float* mean, const float* rstd, const void* gamma,
                               void* dz_out, void* dx_out, float* part_dgamma, float* part_dbeta, float* part_dbias,
@@ -512,6 +692,12 @@ extern "C" int dle_add_ln_bwd(const void* dy, const void* z, const float* mean, 
     if (dropout_p == 0.f && dz_out == nullptr) { dz_out = dx_out; dx_out = nullptr; }   // dx == dz without dropout
     const uint32_t th = dropout_p > 0.f ? dropout_thresh16(dropout_p) : 0u;
     const float sc = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
+    if (H % 512 == 0 && !ln_force_one_warp()) {
+        if (H == 1024) add_ln_bwd2_kernel<2><<<ln2_grid(T), LN2_THREADS, 0, S_(stream)>>>(B_(dy), B_(z), mean, rstd, B_(gamma), BM_(dz_out), BM_(dx_out), part_dgamma, part_dbeta, part_dbias, T, th, sc, seed, dropout_stream);
+        else add_ln_bwd2_kernel<1><<<ln2_grid(T), LN2_THREADS, 0, S_(stream)>>>(B_(dy), B_(z), mean, rstd, B_(gamma), BM_(dz_out), BM_(dx_out), part_dgamma, part_dbeta, part_dbias, T, th, sc, seed, dropout_stream);
+        DLE_LAUNCH_CHECK();
+        return DLE_OK;
+    }
     LN_DISPATCH(H, (add_ln_bwd_kernel<J><<<ln_grid(T), LN_THREADS, 0, S_(stream)>>>(B_(dy), B_(z), mean, rstd, B_(gamma), BM_(dz_out),
                     BM_(dx_out), part_dgamma, part_dbeta, part_dbias, T, th, sc, seed, dropout_stream)));
     DLE_LAUNCH_CHECK();

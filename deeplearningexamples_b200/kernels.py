@@ -129,7 +129,7 @@ def add_ln_bwd(dy, z, mean, rstd, gamma, *, dropout_p=0.0, seed=0, dropout_strea
     """returns dz, dx (== dz when no dropout), dgamma, dbeta, dbias (fp32 [H] each)."""
     lib = L.load()
     T, H = dy.shape
-    n_part = lib.dle_ln_bwd_partials(T)
+    n_part = lib.dle_ln_bwd_partials_h(T, H)
     parts = torch.empty((3, n_part, H), device=dy.device, dtype=torch.float32)
     dz = torch.empty_like(dy)
     dx = torch.empty_like(dy) if dropout_p > 0.0 else None

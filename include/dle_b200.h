@@ -115,7 +115,8 @@ int dle_add_ln_fwd(const void* x, const void* bias, const void* residual, const 
  * and dx_out may be NULL).  dz is also the gradient of the residual branch.  Column reductions are written as fp32 partials [n_part, H] into the caller's workspace:
  *   part_dgamma, part_dbeta, part_dbias (sum_t dx).  n_part = dle_ln_bwd_partials(T).  A second
  *   call dle_colsum_finalize reduces them to bf16/fp32 gradients. */
-int dle_ln_bwd_partials(int64_t T);
+int dle_ln_bwd_partials(int64_t T);             /* upper bound over H (workspace sizing) */
+int dle_ln_bwd_partials_h(int64_t T, int32_t H); /* rows of partials actually written for this H */
 int dle_add_ln_bwd(const void* dy, const void* z, const float* mean, const float* rstd, const void* gamma,
                    void* dz_out, void* dx_out, float* part_dgamma, float* part_dbeta, float* part_dbias,
                    int64_t T, int32_t H, float dropout_p, uint64_t seed, uint32_t dropout_stream, void* stream);
