@@ -74,7 +74,7 @@ __device__ __forceinline__ float gelu_tanh_grad(float x) {
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-7: counter-based RNG, so forward and backward regenerate identical dropout masks
 // from (seed, stream, element-group index) with no mask tensor in HBM.
-// One call -> 128 random bits -> eight 16-bit lanes -> keep decisions for 8 consecutive elements.
+// One call -> four 32-bit words -> (LCG expansion) -> keep decisions for 32 consecutive elements.
 // ---------------------------------------------------------------------------------------------
 template <int ROUNDS>
 __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
@@ -87,20 +87,6 @@ __device__ __forceinline__ uint4 philox4x32(uint4 ctr, uint2 key) {
         key.x += W0; key.y += W1;
     }
     return ctr;
-}
-// keep-mask (bit i set = keep element i of the 8-element group `group`), P(drop) = thresh16/65536.
-// ROUNDS = 7 is the Crush-resistant minimum of Salmon et al. (Random123); the generator is a visible share of the
-// softmax / epilogue instruction streams, so the 3 rounds of extra safety margin of Philox-10 are not spent here.
-template <int ROUNDS = 7>
-__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint32_t stream, uint64_t group, uint32_t thresh16) {
-    uint4 r = philox4x32<ROUNDS>(make_uint4((uint32_t)group, (uint32_t)(group >> 32), stream, 0x5eedu),
-                            make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-    uint32_t m = 0;
-    m |= ((r.x & 0xffffu) >= thresh16) << 0; m |= ((r.x >> 16) >= thresh16) << 1;
-    m |= ((r.y & 0xffffu) >= thresh16) << 2; m |= ((r.y >> 16) >= thresh16) << 3;
-    m |= ((r.z & 0xffffu) >= thresh16) << 4; m |= ((r.z >> 16) >= thresh16) << 5;
-    m |= ((r.w & 0xffffu) >= thresh16) << 6; m |= ((r.w >> 16) >= thresh16) << 7;
-    return m;
 }
 // 32 keep-bits for the 32 consecutive elements of group `group32` (element index >> 5): ONE Philox4x32-7 call gives four
 // independent 32-bit words; each word seeds a 32-bit LCG (x <- x*747796405 + 2891336453, PCG's multiplier/increment) that is
