@@ -66,6 +66,7 @@ SIGNATURES = {
     "dle_lamb_plan_update": (_i32, [_vp, ctypes.POINTER(LambTensor), _i32, _vp]),
     "dle_lamb_step": (_i32, [_vp, _vp, _f32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "dle_lamb_grad_norm": (_i32, [_vp, _vp, _vp, _vp]),
+    "dle_adam_step": (_i32, [_vp, _vp, _f32, _f32, _i32, _vp, _vp, _vp]),
 }
 
 _ERRORS = {-22: "DLE_ERR_INVALID (bad shape/alignment/null pointer)", -5: "DLE_ERR_CUDA (launch/driver failure)",

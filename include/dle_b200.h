@@ -206,6 +206,13 @@ int dle_lamb_plan_update(void* plan, const dle_lamb_tensor* host_tensors, int32_
  * per_tensor_norms_out: optional device fp32 [2*n_tensors] (param norms then update norms). */
 int dle_lamb_step(void* plan, const float* scale, float max_grad_norm, int32_t adam_w_mode, int32_t use_nvlamb,
                   float* found_inf_out, float* global_grad_norm_out, float* per_tensor_norms_out, void* stream);
+/* Multi-tensor Adam / AdamW (+ global-norm clipping) on a plan built by dle_lamb_plan_create (the group's `grad_averaging`
+ * is ignored; `bias_correction` selects 1-beta^t corrections).  max_grad_norm <= 0 disables clipping; clip_eps = 1e-6 reproduces
+ * the SQuAD GradientClipper's coef = max/(norm + 1e-6).
+ * replaces: apex.optimizers.FusedAdam(..., bias_correction=False) + GradientClipper (amp_C.multi_tensor_l2norm / multi_tensor_scale)
+ *   at run_squad.py:703-724,969-975,1092-1099.  Two launches: grad pass + one fused apply pass. */
+int dle_adam_step(void* plan, const float* scale, float max_grad_norm, float clip_eps, int32_t adam_w_mode,
+                  float* found_inf_out, float* global_grad_norm_out, void* stream);
 /* standalone multi-tensor L2 norm over the plan's gradients (fused_lamb_CUDA.multi_tensor_l2norm) */
 int dle_lamb_grad_norm(void* plan, float* norm_out, float* found_inf_out, void* stream);
 

@@ -159,3 +159,40 @@ def poly_warmup_lr(step_after, total_steps, warmup, base_lr, degree=0.5):
     if progress < f(warmup):
         return float(f(base_lr) * progress / f(warmup))
     return float(f(base_lr) * np.power(f(1.0) - progress, f(degree)))
+
+
+def adam_step_numpy(groups, *, scale=1.0, max_grad_norm=0.0, clip_eps=1e-6, adam_w_mode=True):
+    """CPU oracle for the SQuAD optimizer step: GradientClipper (run_squad.py:716-724: coef = max/(norm + 1e-6), applied when
+    < 1) followed by Adam/AdamW as apex.optimizers.FusedAdam is called at run_squad.py:973-975 (bias_correction=False there).
+    apex is not vendored in /root/reference (unpinned): the arithmetic is the published Adam/AdamW update, pinned against
+    torch.optim.AdamW in tests/test_lamb_oracle.py.  fp32 element math, double norm."""
+    f = np.float32
+    tot = sum(float(np.sum(a.astype(np.float64) ** 2)) for g in groups for a in g["grads"])
+    finite = all(np.isfinite(a).all() for g in groups for a in g["grads"])
+    gnorm = f(np.sqrt(tot))
+    if not finite or not np.isfinite(gnorm):
+        return dict(found_inf=True, global_grad_norm=float(gnorm))
+    inv_scale = f(1.0 / np.float64(f(scale)))
+    clip = f(1.0)
+    if max_grad_norm > 0:
+        max_norm = f(max_grad_norm) * f(scale)
+        num = gnorm + f(clip_eps) * f(scale)
+        if num > max_norm:
+            clip = f(num / max_norm)
+    for g in groups:
+        g["step"] = int(g["step"]) + 1
+        b1, b2 = f(g["betas"][0]), f(g["betas"][1])
+        bc1 = f(1.0) - f(np.power(b1, f(g["step"]))) if g.get("bias_correction", True) else f(1.0)
+        bc2 = f(1.0) - f(np.power(b2, f(g["step"]))) if g.get("bias_correction", True) else f(1.0)
+        wd, eps, lr = f(g["weight_decay"]), f(g["eps"]), f(g["lr"])
+        for p, gr, m, v in zip(g["params"], g["grads"], g["exp_avg"], g["exp_avg_sq"]):
+            sg = (gr * inv_scale) / clip
+            if not adam_w_mode:
+                sg = sg + wd * p
+            m[...] = m * b1 + (f(1.0) - b1) * sg
+            v[...] = v * b2 + (f(1.0) - b2) * sg * sg
+            upd = (m / bc1) / (np.sqrt(v / bc2) + eps)
+            if adam_w_mode:
+                upd = upd + wd * p
+            p[...] = p - lr * upd.astype(np.float32)
+    return dict(found_inf=False, global_grad_norm=float(gnorm))

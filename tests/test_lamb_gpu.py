@@ -198,3 +198,35 @@ def test_oracle_vs_reference_kernel():
         np.testing.assert_allclose(opt.state[ours[i]]['exp_avg'].cpu().numpy(), og[0]["exp_avg"][i], rtol=1e-5, atol=1e-9)
         np.testing.assert_allclose(opt.state[ours[i]]['exp_avg_sq'].cpu().numpy(), og[0]["exp_avg_sq"][i], rtol=1e-5, atol=1e-12)
         np.testing.assert_allclose(ours[i].detach().cpu().numpy(), og[0]["params"][i], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fused_adam_matches_oracle(dtype):
+    """dle_adam_step (SQuAD fine-tune optimizer: clip + Adam, bias_correction=False) vs the CPU oracle."""
+    from deeplearningexamples_b200.adam import FusedAdam
+    from oracle import lamb_oracle as LO
+    params, rng = _make(dtype, seed=7)
+    opt = FusedAdam([{'params': params[0], 'weight_decay': 0.01}, {'params': params[1], 'weight_decay': 0.0}], lr=3e-3,
+                    bias_correction=False, max_grad_norm=1.0)
+    opt.setup_fp32_params()
+    og = [dict(params=[p.detach().float().cpu().numpy().copy() for p in grp], grads=None,
+               exp_avg=[np.zeros(tuple(p.shape), np.float32) for p in grp], exp_avg_sq=[np.zeros(tuple(p.shape), np.float32) for p in grp],
+               lr=3e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd, step=0, bias_correction=False) for grp, wd in zip(params, (0.01, 0.0))]
+    for it in range(4):
+        mag = 5.0 if it == 1 else 1e-2                    # iteration 1 clips
+        for grp, ogrp in zip(params, og):
+            ogrp["grads"] = []
+            for p in grp:
+                g = torch.from_numpy(rng.standard_normal(tuple(p.shape)).astype(np.float32) * mag).cuda().to(dtype)
+                p.grad = g
+                ogrp["grads"].append(g.float().cpu().numpy())
+        opt.step()
+        r = LO.adam_step_numpy(og, max_grad_norm=1.0)
+        assert opt._global_grad_norm.item() == pytest.approx(r["global_grad_norm"], rel=1e-5)
+    for gi, (grp, ogrp) in enumerate(zip(params, og)):
+        for pi, p in enumerate(grp):
+            st = opt.state[p]
+            np.testing.assert_allclose(st['exp_avg'].cpu().numpy(), ogrp["exp_avg"][pi], rtol=1e-5, atol=1e-9)
+            np.testing.assert_allclose(st['exp_avg_sq'].cpu().numpy(), ogrp["exp_avg_sq"][pi], rtol=1e-5, atol=1e-12)
+            master = opt.param_groups_fp32[gi]['params'][pi] if dtype == torch.bfloat16 else p.data
+            np.testing.assert_allclose(master.cpu().numpy(), ogrp["params"][pi], rtol=2e-5, atol=2e-6)

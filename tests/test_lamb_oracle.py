@@ -101,3 +101,37 @@ def test_poly_warmup_schedule():
     assert LO.poly_warmup_lr(0, 100, 0.1, 1.0) == pytest.approx(0.1, rel=1e-6)
     assert LO.poly_warmup_lr(8, 100, 0.1, 1.0) == pytest.approx(0.9, rel=1e-6)
     assert LO.poly_warmup_lr(49, 100, 0.1, 1.0) == pytest.approx((1 - 0.5) ** 0.5, rel=1e-6)
+
+
+def test_adam_oracle_matches_torch_adamw():
+    """Pins oracle.adam_step_numpy (the SQuAD FusedAdam/clip restatement) to torch.optim.AdamW (decoupled decay, bias correction)."""
+    import torch
+    rng = np.random.default_rng(3)
+    shapes = [(17, 5), (64,), (3, 3, 3)]
+    ps = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    tps = [torch.nn.Parameter(torch.from_numpy(p.copy())) for p in ps]
+    opt = torch.optim.AdamW(tps, lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    grp = dict(params=[p.copy() for p in ps], grads=None, exp_avg=[np.zeros_like(p) for p in ps], exp_avg_sq=[np.zeros_like(p) for p in ps],
+               lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, step=0, bias_correction=True)
+    for it in range(4):
+        gs = [rng.standard_normal(s).astype(np.float32) * 0.1 for s in shapes]
+        for tp, g in zip(tps, gs):
+            tp.grad = torch.from_numpy(g.copy())
+        opt.step()
+        grp["grads"] = gs
+        LO.adam_step_numpy([grp], max_grad_norm=0.0)
+    for tp, p in zip(tps, grp["params"]):
+        np.testing.assert_allclose(tp.detach().numpy(), p, rtol=2e-5, atol=1e-7)
+
+
+def test_adam_oracle_clip_matches_squad_clipper():
+    """GradientClipper: grads scaled by max/(norm+1e-6) when that is < 1 (run_squad.py:721-724)."""
+    g = np.full(16, 2.0, np.float32)                      # norm 8 > max 1
+    mk = lambda grads: dict(params=[np.zeros(16, np.float32)], grads=[grads], exp_avg=[np.zeros(16, np.float32)],
+                            exp_avg_sq=[np.zeros(16, np.float32)], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, step=0,
+                            bias_correction=False)
+    a, b = mk(g.copy()), mk(g * np.float32(1.0 / (8.0 + 1e-6)))
+    LO.adam_step_numpy([a], max_grad_norm=1.0)
+    LO.adam_step_numpy([b], max_grad_norm=0.0)
+    np.testing.assert_allclose(a["exp_avg"][0], b["exp_avg"][0], rtol=1e-6)
+    np.testing.assert_allclose(a["params"][0], b["params"][0], rtol=1e-5)

@@ -222,3 +222,46 @@ def test_fused_layer_equals_modular_composition(small):
             continue                                    # analytically zero gradient: both sides are rounding noise
         a, c = res[0][1][k], res[1][1][k]
         assert (a - c).abs().max().item() <= 2e-2 * c.abs().max().item() + 1e-6, k
+
+
+def test_squad_head_forward_backward_vs_oracle():
+    """BASELINE configs[3] shape (seq 384, QA head): BertForQuestionAnswering over the same encoder kernels vs the CPU oracle,
+    and one FusedAdam + clip step (the SQuAD optimizer)."""
+    from deeplearningexamples_b200 import modeling
+    from deeplearningexamples_b200.adam import FusedAdam
+    from oracle import bert_oracle as O
+    cfg = dict(hidden_size=256, num_hidden_layers=2, num_attention_heads=4, intermediate_size=1024, vocab_size=1024,
+               max_position_embeddings=512, type_vocab_size=2, hidden_act="gelu", initializer_range=0.02,
+               hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    sd = O.bf16_representable_params(cfg, seed=5)
+    g = torch.Generator().manual_seed(6)
+    qa_w = (torch.randn(2, 256, generator=g) * 0.05).to(bf).float()
+    qa_b = torch.zeros(2)
+    B, S = 2, 384
+    batch = O.synthetic_batch(B, S, cfg["vocab_size"], 1, seed=8, full_mask=False)
+    start, end = torch.randint(0, S, (B,), generator=g), torch.randint(0, S, (B,), generator=g)
+    with torch.no_grad():
+        seq, _ = O.bert_model(sd, cfg, batch["input_ids"], batch["token_type_ids"], batch["attention_mask"])
+        logits_ref = torch.nn.functional.linear(seq, qa_w, qa_b)           # modeling.py:1366-1369
+    m = modeling.BertForQuestionAnswering(modeling.BertConfig.from_dict(cfg))
+    full = {k: v for k, v in sd.items() if k.startswith("bert.")}
+    full["qa_outputs.weight"], full["qa_outputs.bias"] = qa_w, qa_b
+    missing, unexpected = m.load_state_dict(full, strict=False)
+    assert not missing and not unexpected, (missing, unexpected)
+    m = m.cuda().to(bf).train()
+    s_log, e_log = m(batch["input_ids"].cuda(), batch["token_type_ids"].cuda(), batch["attention_mask"].cuda())
+    assert _rel_l2(s_log.cpu(), logits_ref[..., 0]) < 1e-2 and _rel_l2(e_log.cpu(), logits_ref[..., 1]) < 1e-2
+    lf = torch.nn.CrossEntropyLoss()
+    loss = (lf(s_log.float(), start.cuda()) + lf(e_log.float(), end.cuda())) / 2     # run_squad.py:1077-1080
+    loss.backward()
+    no_decay = ['bias', 'LayerNorm.bias', 'LayerNorm.weight']                          # run_squad.py:960-964
+    named = list(m.named_parameters())
+    opt = FusedAdam([{'params': [p for n, p in named if not any(nd in n for nd in no_decay)], 'weight_decay': 0.01},
+                     {'params': [p for n, p in named if any(nd in n for nd in no_decay)], 'weight_decay': 0.0}], lr=3e-5,
+                    bias_correction=False, max_grad_norm=1.0)
+    opt.setup_fp32_params()
+    before = named[10][1].detach().clone()
+    opt.step()
+    torch.cuda.synchronize()
+    assert opt.param_groups[0]['step'].item() == 1 and opt._found_inf.item() == 0.0
+    assert not torch.equal(before, named[10][1].detach())

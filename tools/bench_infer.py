@@ -1,0 +1,30 @@
+"""Encoder-only inference throughput (BASELINE.json configs[4]: BERT-large, S=512, B=256, bf16, eval mode, 1xB200):
+embeddings + 24 encoder layers + pooler, forward only, CUDA-event timed.  FasterTransformer is a README stub in the reference
+(SURVEY.md 0), so the parity target for this config is the reference BertModel in eval mode = the CPU oracle (tests/test_model_gpu.py)."""
+import json, os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from deeplearningexamples_b200 import modeling, training as T
+
+B, S = int(os.environ.get("B", 256)), int(os.environ.get("S", 512))
+cfg = dict(T.BERT_LARGE); cfg["vocab_size"] = 30528
+torch.manual_seed(0)
+model = modeling.BertModel(modeling.BertConfig.from_dict(cfg)).cuda().to(torch.bfloat16).eval()
+batch = T.synthetic_batch(B, S, cfg["vocab_size"], 1, seed=1, device="cuda")
+def step():
+    with torch.no_grad():
+        return model(batch["input_ids"], batch["token_type_ids"], batch["attention_mask"])
+for _ in range(3): step()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+n = 8
+e0.record()
+for _ in range(n): step()
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / n
+L_, H, I = 24, 1024, 4096
+fwd = L_ * (6 * S * H * H + 4 * S * S * H + 2 * S * H * H + 4 * S * H * I)
+out = dict(workload=f"BERT-large encoder-only inference seq{S} bs{B} bf16", ms_per_batch=round(ms, 2), sequences_per_s=round(B / ms * 1e3, 1),
+           tflops=round(B * fwd / ms / 1e9, 1))
+print(json.dumps(out))
+os.makedirs("gpurun_out", exist_ok=True); json.dump(out, open("gpurun_out/bench_infer.json", "w"))
