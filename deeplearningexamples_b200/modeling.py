@@ -126,46 +126,42 @@ class LinearActivation(nn.Module):
 
 
 class BertConfig(object):
-    """Configuration of a `BertModel` (reference modeling.py:168-261): JSON <-> attribute bag."""
+    """Configuration of a `BertModel`: an attribute bag that round-trips through JSON.
 
-    def __init__(self, vocab_size_or_config_json_file, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
-                 intermediate_size=3072, hidden_act="gelu", hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1,
-                 max_position_embeddings=512, type_vocab_size=2, initializer_range=0.02, output_all_encoded_layers=False):
+    Same constructor contract as the reference class (modeling.py:168-261): the first argument is either the vocabulary size (the
+    remaining hyper-parameters then come from keyword arguments / defaults) or the path of a JSON file whose keys become attributes.
+    `from_dict` / `from_json_file` / `to_dict` / `to_json_string` / `to_json_file` behave as there.
+    """
+    _DEFAULTS = (("hidden_size", 768), ("num_hidden_layers", 12), ("num_attention_heads", 12), ("intermediate_size", 3072),
+                 ("hidden_act", "gelu"), ("hidden_dropout_prob", 0.1), ("attention_probs_dropout_prob", 0.1),
+                 ("max_position_embeddings", 512), ("type_vocab_size", 2), ("initializer_range", 0.02),
+                 ("output_all_encoded_layers", False))
+
+    def __init__(self, vocab_size_or_config_json_file, **hyper):
+        unknown = set(hyper) - {k for k, _ in self._DEFAULTS}
+        if unknown:
+            raise TypeError("unexpected BertConfig arguments: %s" % sorted(unknown))
         if isinstance(vocab_size_or_config_json_file, str):
-            with open(vocab_size_or_config_json_file, "r", encoding='utf-8') as reader:
-                for key, value in json.loads(reader.read()).items():
-                    self.__dict__[key] = value
+            with open(vocab_size_or_config_json_file, "r", encoding="utf-8") as fh:
+                self.__dict__.update(json.load(fh))
         elif isinstance(vocab_size_or_config_json_file, int):
             self.vocab_size = vocab_size_or_config_json_file
-            self.hidden_size = hidden_size
-            self.num_hidden_layers = num_hidden_layers
-            self.num_attention_heads = num_attention_heads
-            self.hidden_act = hidden_act
-            self.intermediate_size = intermediate_size
-            self.hidden_dropout_prob = hidden_dropout_prob
-            self.attention_probs_dropout_prob = attention_probs_dropout_prob
-            self.max_position_embeddings = max_position_embeddings
-            self.type_vocab_size = type_vocab_size
-            self.initializer_range = initializer_range
-            self.output_all_encoded_layers = output_all_encoded_layers
+            for key, default in self._DEFAULTS:
+                setattr(self, key, hyper.get(key, default))
         else:
             raise ValueError("First argument must be either a vocabulary size (int)"
                              "or the path to a pretrained model config file (str)")
 
     @classmethod
     def from_dict(cls, json_object):
-        config = BertConfig(vocab_size_or_config_json_file=-1)
-        for key, value in json_object.items():
-            config.__dict__[key] = value
+        config = cls(vocab_size_or_config_json_file=-1)
+        config.__dict__.update(json_object)
         return config
 
     @classmethod
     def from_json_file(cls, json_file):
-        with open(json_file, "r", encoding='utf-8') as reader:
-            return cls.from_dict(json.loads(reader.read()))
-
-    def __repr__(self):
-        return str(self.to_json_string())
+        with open(json_file, "r", encoding="utf-8") as fh:
+            return cls.from_dict(json.load(fh))
 
     def to_dict(self):
         return copy.deepcopy(self.__dict__)
@@ -174,8 +170,11 @@ class BertConfig(object):
         return json.dumps(self.to_dict(), indent=2, sort_keys=True) + "\n"
 
     def to_json_file(self, json_file_path):
-        with open(json_file_path, "w", encoding='utf-8') as writer:
-            writer.write(self.to_json_string())
+        with open(json_file_path, "w", encoding="utf-8") as fh:
+            fh.write(self.to_json_string())
+
+    def __repr__(self):
+        return self.to_json_string()
 
 
 class BertEmbeddings(nn.Module):
