@@ -494,12 +494,19 @@ class BertPreTrainingHeads(nn.Module):
         self.predictions = BertLMPredictionHead(config, bert_model_embedding_weights)
         self.seq_relationship = nn.Linear(config.hidden_size, 2)
         self.sequence_output_is_dense = sequence_output_is_dense
+        # Optional static bound on the number of masked positions per batch (batch * max_predictions_per_seq).  When set, the row
+        # indices come from torch.nonzero_static: no device->host sync (the reference's torch.nonzero drains the launch queue once
+        # per step).  Surplus slots point at token 0 ([CLS], never masked => label -1 => ignored by the criterion).
+        self.static_masked_count = None
 
     def forward(self, sequence_output, pooled_output, masked_lm_labels):
         if self.sequence_output_is_dense:
             # only the masked positions reach the vocabulary GEMM (reference modeling.py:588-591); bit-exact row gather
             flat = sequence_output.reshape(-1, sequence_output.shape[-1])
-            idx = torch.nonzero(masked_lm_labels.view(-1) != -1).squeeze(-1)
+            if self.static_masked_count:
+                idx = torch.nonzero_static(masked_lm_labels.view(-1) != -1, size=int(self.static_masked_count), fill_value=0).squeeze(-1)
+            else:
+                idx = torch.nonzero(masked_lm_labels.view(-1) != -1).squeeze(-1)
             prediction_scores = self.predictions(ops.GatherRowsFn.apply(flat, idx))
         else:
             prediction_scores = self.predictions(sequence_output)

@@ -176,6 +176,8 @@ def prepare_model_and_optimizer(args, device, sequence_output_is_dense):
     if config.vocab_size % 8 != 0:
         config.vocab_size += 8 - (config.vocab_size % 8)
     model = modeling.BertForPreTraining(config, sequence_output_is_dense=sequence_output_is_dense)
+    if sequence_output_is_dense:      # max_predictions_per_seq bounds the masked positions per sequence by definition of the data
+        model.cls.static_masked_count = (args.train_batch_size) * args.max_predictions_per_seq
     checkpoint, global_step = None, 0
     if args.resume_from_checkpoint:
         if args.resume_step == -1 and not args.init_checkpoint:

@@ -41,8 +41,13 @@ class BertPretrainingCriterion(torch.nn.Module):
 
     def forward(self, prediction_scores, seq_relationship_score, masked_lm_labels, next_sentence_labels):
         if self.sequence_output_is_dense:
+            # reference: labels[labels != -1] (boolean indexing => host sync).  Same rows, same order, without the sync: the
+            # first `n` non-ignored positions, n = rows of the (already dense) prediction scores; surplus slots (static-count
+            # mode) read position 0, whose label is -1 and is ignored by the loss.
             flat = masked_lm_labels.view(-1)
-            mlm_labels = flat[flat != -1]
+            n = prediction_scores.view(-1, self.vocab_size).shape[0]
+            idx = torch.nonzero_static(flat != -1, size=n, fill_value=0).squeeze(-1)
+            mlm_labels = flat[idx]
             masked_lm_loss = self.loss_fn(prediction_scores.view(-1, self.vocab_size), mlm_labels.view(-1))
         else:
             masked_lm_loss = self.loss_fn(prediction_scores.view(-1, self.vocab_size), masked_lm_labels.view(-1))
@@ -77,13 +82,15 @@ def synthetic_batch(B, S, vocab, max_pred, seed=42, full_mask=True, device="cpu"
 
 def prepare_model_and_optimizer(config_dict, device, *, learning_rate=6e-3, warmup_proportion=0.2843, max_steps=7038,
                                 sequence_output_is_dense=True, init_loss_scale=2 ** 20, use_grad_scaler=True,
-                                distributed=False, bucket_cap_mb=100, dtype=torch.bfloat16, seed=42):
+                                distributed=False, bucket_cap_mb=100, dtype=torch.bfloat16, seed=42, static_masked_count=None):
     cfg = dict(config_dict)
     if cfg["vocab_size"] % 8 != 0:                       # run_pretraining.py:383-384
         cfg["vocab_size"] += 8 - (cfg["vocab_size"] % 8)
     config = modeling.BertConfig.from_dict(cfg)
     torch.manual_seed(seed)
     model = modeling.BertForPreTraining(config, sequence_output_is_dense=sequence_output_is_dense)
+    if static_masked_count:
+        model.cls.static_masked_count = int(static_masked_count)
     model.to(device)
     model.to(dtype)                                       # the reference's model.half() (:416-417), in bf16
     no_decay = ['bias', 'gamma', 'beta', 'LayerNorm']     # :422-427

@@ -265,3 +265,21 @@ def test_squad_head_forward_backward_vs_oracle():
     torch.cuda.synchronize()
     assert opt.param_groups[0]['step'].item() == 1 and opt._found_inf.item() == 0.0
     assert not torch.equal(before, named[10][1].detach())
+
+
+def test_static_masked_count_is_equivalent_and_sync_free(small):
+    """nonzero_static(batch*max_pred) gathers the same rows as torch.nonzero; surplus slots are ignored by the criterion."""
+    from deeplearningexamples_b200.training import BertPretrainingCriterion
+    gold, sd, batch = small
+    b = {k: v.cuda() for k, v in batch.items()}
+    m = _build(gold["cfg"], sd)
+    crit = BertPretrainingCriterion(gold["cfg"]["vocab_size"], sequence_output_is_dense=True)
+    s_dyn, n_dyn = m(b["input_ids"], b["token_type_ids"], b["attention_mask"], b["labels"])
+    l_dyn = crit(s_dyn, n_dyn, b["labels"], b["next_sentence_labels"])
+    m.cls.static_masked_count = 2 * 16                       # upper bound: 10 masked per sequence in this batch
+    s_st, n_st = m(b["input_ids"], b["token_type_ids"], b["attention_mask"], b["labels"])
+    assert s_st.shape[0] == 32 and torch.equal(s_st[:20], s_dyn)
+    l_st = crit(s_st, n_st, b["labels"], b["next_sentence_labels"])
+    assert abs(l_st.item() - l_dyn.item()) < 1e-3 * abs(l_dyn.item())
+    l_st.backward()
+    assert m.bert.embeddings.word_embeddings.weight.grad is not None
