@@ -23,7 +23,7 @@ class GemmArgs(ctypes.Structure):
                 ("M", _i32), ("N", _i32), ("K", _i32), ("a_layout", _i32), ("b_layout", _i32),
                 ("lda", _i64), ("ldb", _i64), ("ldo", _i64), ("ldo2", _i64), ("ld_aux", _i64),
                 ("epilogue", _i32), ("splits", _i32), ("tile_n", _i32), ("alpha", _f32),
-                ("dropout_p", _f32), ("dropout_stream", _u32), ("seed", _u64)]
+                ("dropout_p", _f32), ("dropout_stream", _u32), ("seed", _u64), ("colsum_out", _vp)]
 
 
 class LambTensor(ctypes.Structure):
@@ -41,7 +41,7 @@ SIGNATURES = {
     "dle_version": (_i32, [ctypes.c_char_p, _i32]),
     "dle_gemm_bf16": (_i32, [ctypes.POINTER(GemmArgs), _vp]),
     "dle_attn_fwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _u64, _u32, _vp]),
-    "dle_attn_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _u64, _u32, _vp]),
+    "dle_attn_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _u64, _u32, _vp]),
     "dle_add_ln_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _u64, _u32, _vp]),
     "dle_ln_bwd_partials": (_i32, [_i64]),
     "dle_ln_bwd_partials_h": (_i32, [_i64, _i32]),

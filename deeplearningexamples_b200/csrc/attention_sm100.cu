@@ -291,6 +291,7 @@ constexpr int BWD_COMPUTE_THREADS = 512;   // 4 warps per TMEM lane quarter, eac
 
 struct AttnBwdParams {
     const float* mask; const float* lse; const float* delta;
+    float* dbias;          // [3H] fp32 or null: += column sums of dqkv
     bf16* dqkv;            // [T, 3H]
     int B, S, A, H;
     int tok_stride_s, tok_stride_b;
@@ -534,6 +535,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
                 for (int k = 0; k < 32; k += 8)
                     st_global_v4(o + k, pack_bf16(__uint_as_float(v[k]), __uint_as_float(v[k + 1])), pack_bf16(__uint_as_float(v[k + 2]), __uint_as_float(v[k + 3])),
                                  pack_bf16(__uint_as_float(v[k + 4]), __uint_as_float(v[k + 5])), pack_bf16(__uint_as_float(v[k + 6]), __uint_as_float(v[k + 7])));
+                if (p.dbias != nullptr) {                        // key / value bias gradients: column sums of the stored bf16 values
+                    float f[32];
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) f[k] = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[k])));
+                    const float cs = warp_column_sums32(f, lane);
+                    atomicAdd(p.dbias + (which + 1) * p.H + h * HD + hf * 32 + lane, cs);
+                }
             }
             }
             tc_fence_before();
@@ -552,6 +560,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             for (int k = 0; k < 32; k += 8)
                 st_global_v4(o + k, pack_bf16(__uint_as_float(v[k]), __uint_as_float(v[k + 1])), pack_bf16(__uint_as_float(v[k + 2]), __uint_as_float(v[k + 3])),
                              pack_bf16(__uint_as_float(v[k + 4]), __uint_as_float(v[k + 5])), pack_bf16(__uint_as_float(v[k + 6]), __uint_as_float(v[k + 7])));
+            if (p.dbias != nullptr) {                            // query bias gradient
+                float f[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) f[k] = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[k])));
+                const float cs = warp_column_sums32(f, lane);
+                atomicAdd(p.dbias + h * HD + hf * 32 + lane, cs);
+            }
         }
     }
     tc_fence_before();
@@ -611,7 +626,7 @@ extern "C" int dle_attn_fwd(const void* qkv, const float* mask, void* ctx, float
 }
 
 extern "C" int dle_attn_bwd(const void* qkv, const float* mask, const void* ctx, const void* dctx, const float* lse, void* dqkv,
-                            float* delta_ws, int32_t B, int32_t S, int32_t A, int32_t seq_first, float dropout_p, uint64_t seed,
+                            float* delta_ws, float* dbias_qkv, int32_t B, int32_t S, int32_t A, int32_t seq_first, float dropout_p, uint64_t seed,
                             uint32_t dropout_stream, void* stream) {
     DLE_CHECK_ARG(qkv && ctx && dctx && lse && dqkv && delta_ws && attn_check(B, S, A) == DLE_OK && dropout_p >= 0.f && dropout_p < 1.f);
     const int H = A * HD;
@@ -625,7 +640,7 @@ extern "C" int dle_attn_bwd(const void* qkv, const float* mask, const void* ctx,
     attn_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(dctx), reinterpret_cast<const bf16*>(ctx), delta_ws, B, S, A, seq_first);
     DLE_LAUNCH_CHECK();
     AttnBwdParams p;
-    p.mask = mask; p.lse = lse; p.delta = delta_ws; p.dqkv = reinterpret_cast<bf16*>(dqkv);
+    p.mask = mask; p.lse = lse; p.delta = delta_ws; p.dbias = dbias_qkv; p.dqkv = reinterpret_cast<bf16*>(dqkv);
     p.B = B; p.S = S; p.A = A; p.H = H; p.tok_stride_s = seq_first ? B : 1; p.tok_stride_b = seq_first ? 1 : S; p.scale = 0.125f; p.scale_log2 = 0.125f * LOG2E;
     p.drop_thresh = dropout_p > 0.f ? dropout_thresh16(dropout_p) : 0u;
     p.drop_scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;

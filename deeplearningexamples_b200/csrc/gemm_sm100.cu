@@ -47,6 +47,7 @@ struct GemmKernelParams {
     uint32_t drop_stream;
     unsigned long long seed;
     float alpha;
+    float* colsum_out;     // [N] fp32 or null: += column sums of the (bf16-rounded) output, e.g. the bias gradient of the layer below
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -186,6 +187,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
         for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
     }
     warp_store_rows(reinterpret_cast<bf16*>(p.out), p.ldo, row_base, col0, p.M, p.N, stage, lane, v);
+    if (p.colsum_out != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = (row < p.M) ? __bfloat162float(__float2bfloat16_rn(v[i])) : 0.f;
+        const float cs = warp_column_sums32(v, lane);
+        if (lane < ncols) atomicAdd(p.colsum_out + col0 + lane, cs);
+    }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -398,6 +405,7 @@ static int launch_gemm(const dle_gemm_args* a, cudaStream_t stream) {
     p.drop_stream = a->dropout_stream;
     p.seed = a->seed;
     p.alpha = a->alpha;
+    p.colsum_out = reinterpret_cast<float*>(a->colsum_out);
 
     auto kern = gemm_bf16_tcgen05_kernel<BN, A_MN, B_MN>;
     static bool attr_set = false;

@@ -41,7 +41,7 @@ def _row_major_2d(t, name):
 # GEMM
 # ------------------------------------------------------------------------------------------------
 def gemm(a, b, *, a_layout=L.LAYOUT_K, b_layout=L.LAYOUT_K, epilogue=L.EPI_BIAS, bias=None, aux=None,
-         out=None, out2=None, splits=1, tile_n=0, alpha=1.0, dropout_p=0.0, seed=0, dropout_stream=0):
+         out=None, out2=None, splits=1, tile_n=0, alpha=1.0, dropout_p=0.0, seed=0, dropout_stream=0, colsum_out=None):
     """D[M,N] = alpha * A x B^T with fused epilogue (see include/dle_b200.h).
 
     a: [M,K] (LAYOUT_K) or [K,M] (LAYOUT_MN);  b: [N,K] (LAYOUT_K) or [K,N] (LAYOUT_MN)."""
@@ -73,6 +73,7 @@ def gemm(a, b, *, a_layout=L.LAYOUT_K, b_layout=L.LAYOUT_K, epilogue=L.EPI_BIAS,
     args.epilogue, args.splits, args.tile_n = epilogue, splits, tile_n
     args.alpha, args.dropout_p = alpha, dropout_p
     args.dropout_stream, args.seed = dropout_stream, seed
+    args.colsum_out = 0 if colsum_out is None else _req(colsum_out, torch.float32, "colsum_out").data_ptr()
     if gemm_profile is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -98,12 +99,13 @@ def attn_fwd(qkv, mask, B, S, A, dropout_p=0.0, seed=0, dropout_stream=0, seq_fi
     return ctx, lse
 
 
-def attn_bwd(qkv, mask, ctx, dctx, lse, B, S, A, dropout_p=0.0, seed=0, dropout_stream=0, seq_first=False):
+def attn_bwd(qkv, mask, ctx, dctx, lse, B, S, A, dropout_p=0.0, seed=0, dropout_stream=0, seq_first=False, dbias=None):
+    """dbias: optional zeroed fp32 [3H] receiving the column sums of dqkv (q/k/v bias gradients)."""
     lib = L.load()
     dqkv = torch.empty_like(qkv)
     delta = torch.empty((B, A, S), device=qkv.device, dtype=torch.float32)
     L.launch_count["n"] += 2; L.check(lib.dle_attn_bwd(_ptr(qkv), _ptr(mask), _ptr(ctx), _ptr(_req(dctx, bf16, "dctx")), _ptr(lse), _ptr(dqkv),
-                             _ptr(delta), B, S, A, 1 if seq_first else 0, dropout_p, seed, dropout_stream, _stream()), "dle_attn_bwd")
+                             _ptr(delta), _ptr(dbias), B, S, A, 1 if seq_first else 0, dropout_p, seed, dropout_stream, _stream()), "dle_attn_bwd")
     return dqkv
 
 
@@ -125,8 +127,8 @@ def add_ln_fwd(x, gamma, beta, *, bias=None, residual=None, eps=1e-12, dropout_p
     return y, (z if z is not None else x), mean, rstd
 
 
-def add_ln_bwd(dy, z, mean, rstd, gamma, *, dropout_p=0.0, seed=0, dropout_stream=0, want_dbias=True):
-    """returns dz, dx (== dz when no dropout), dgamma, dbeta, dbias (fp32 [H] each)."""
+def add_ln_bwd(dy, z, mean, rstd, gamma, *, dropout_p=0.0, seed=0, dropout_stream=0, want_dbias=True, out_dtype=torch.float32):
+    """returns dz, dx (== dz when no dropout), dgamma, dbeta, dbias ([H] each, fp32 or bf16 per out_dtype)."""
     lib = L.load()
     T, H = dy.shape
     n_part = lib.dle_ln_bwd_partials_h(T, H)
@@ -137,8 +139,8 @@ def add_ln_bwd(dy, z, mean, rstd, gamma, *, dropout_p=0.0, seed=0, dropout_strea
                                _ptr(parts[1]), _ptr(parts[2]) if want_dbias else None, T, H, dropout_p, seed,
                                dropout_stream, _stream()), "dle_add_ln_bwd")
     na = 3 if want_dbias else 2
-    red = torch.empty((na, H), device=dy.device, dtype=torch.float32)
-    L.launch_count["n"] += 1; L.check(lib.dle_colsum_finalize_batched(_ptr(parts), na, n_part, H, _ptr(red), L.DLE_DTYPE_F32, 0, _stream()),
+    red = torch.empty((na, H), device=dy.device, dtype=out_dtype)
+    L.launch_count["n"] += 1; L.check(lib.dle_colsum_finalize_batched(_ptr(parts), na, n_part, H, _ptr(red), L.DLE_DTYPE_F32 if out_dtype == torch.float32 else L.DLE_DTYPE_BF16, 0, _stream()),
                                       "dle_colsum_finalize_batched")
     return (dz, dx if dx is not None else dz, *red.unbind(0))
 

@@ -228,24 +228,31 @@ class BertLayerFn(torch.autograd.Function):
         wq, bq, wo, bo, g1, be1, w1, b1, w2, b2, g2, be2 = ctx.params
         B, S, A, p_attn, p_hid, eps, sid_attn, sid_h1, sid_h2, seq_first = ctx.cfg
         seed_a, seed_1, seed_2 = ctx.seeds
+        H_ = x.shape[1]
+        # bias gradients of FFN1 (4H) and q|k|v (3H) are column sums of tensors produced below: the producing kernels accumulate
+        # them (warp transpose-reduce + red.add) instead of a separate pass re-reading du / dqkv from HBM
+        bias_acc = torch.zeros(w1.shape[0] + 3 * H_, device=x.device, dtype=torch.float32)
+        db1_acc, dbqkv_acc = bias_acc[:w1.shape[0]], bias_acc[w1.shape[0]:]
         # ---- BertOutput
         dz2, dh2, dg2, dbe2, db2 = K.add_ln_bwd(dy2.contiguous(), z2, mean2, rstd2, w16(g2), dropout_p=p_hid, seed=seed_2,
-                                                dropout_stream=sid_h2)
-        du = K.gemm(dh2, w16(w2), b_layout=L.LAYOUT_MN, epilogue=L.EPI_DGELU, aux=u)          # dgrad * gelu'(u)
+                                                dropout_stream=sid_h2, out_dtype=g2.dtype)
+        du = K.gemm(dh2, w16(w2), b_layout=L.LAYOUT_MN, epilogue=L.EPI_DGELU, aux=u, colsum_out=db1_acc)   # dgrad * gelu'(u)
         dw2 = wgrad(dh2, g, w2.dtype)
         # ---- BertIntermediate (+ residual branch of BertOutput folded into the epilogue)
         dy1 = K.gemm(du, w16(w1), b_layout=L.LAYOUT_MN, epilogue=L.EPI_ADD, aux=dz2)
         dw1 = wgrad(du, y1, w1.dtype)
-        db1 = _to_param_dtype(K.colsum(du), b1)
         # ---- BertSelfOutput
-        dz1, dh1, dg1, dbe1, dbo = K.add_ln_bwd(dy1, z1, mean1, rstd1, w16(g1), dropout_p=p_hid, seed=seed_1, dropout_stream=sid_h1)
+        dz1, dh1, dg1, dbe1, dbo = K.add_ln_bwd(dy1, z1, mean1, rstd1, w16(g1), dropout_p=p_hid, seed=seed_1, dropout_stream=sid_h1,
+                                                out_dtype=g1.dtype)
         datt = K.gemm(dh1, w16(wo), b_layout=L.LAYOUT_MN)
         dwo = wgrad(dh1, att, wo.dtype)
         # ---- BertSelfAttention (+ residual branch of BertSelfOutput folded into the QKV dgrad epilogue)
-        dqkv = K.attn_bwd(qkv, mask, att, datt, lse, B, S, A, dropout_p=p_attn, seed=seed_a, dropout_stream=sid_attn, seq_first=seq_first)
+        dqkv = K.attn_bwd(qkv, mask, att, datt, lse, B, S, A, dropout_p=p_attn, seed=seed_a, dropout_stream=sid_attn, seq_first=seq_first,
+                          dbias=dbqkv_acc)
         dx = K.gemm(dqkv, w16(w_qkv, key=wq), b_layout=L.LAYOUT_MN, epilogue=L.EPI_ADD, aux=dz1)
         dwqkv = wgrad(dqkv, x, wq.dtype)
-        dbqkv = _to_param_dtype(K.colsum(dqkv), bq)
+        bias_g = bias_acc if b1.dtype == torch.float32 else bias_acc.to(b1.dtype)
+        db1, dbqkv = bias_g[:w1.shape[0]], bias_g[w1.shape[0]:]
         H = dwqkv.shape[1]
         c = _to_param_dtype
         return (dx, None, dwqkv[0:H], dwqkv[H:2 * H], dwqkv[2 * H:3 * H], dbqkv[0:H], dbqkv[H:2 * H], dbqkv[2 * H:3 * H],

@@ -76,6 +76,7 @@ typedef struct dle_gemm_args {
     float dropout_p;       /* DLE_EPI_BIAS_DROPOUT_RESIDUAL: drop probability, 0 = off */
     uint32_t dropout_stream; /* RNG stream id (distinct per call site so masks differ per layer) */
     uint64_t seed;
+    void* colsum_out;      /* fp32 [N] or NULL: += column sums of the bf16 output (bias gradient of the producing layer), atomics */
 } dle_gemm_args;
 
 int dle_gemm_bf16(const dle_gemm_args* host_args, void* stream);
@@ -94,9 +95,10 @@ int dle_gemm_bf16(const dle_gemm_args* host_args, void* stream);
  * ------------------------------------------------------------------------------------------ */
 int dle_attn_fwd(const void* qkv, const float* mask, void* ctx, float* lse, int32_t B, int32_t S, int32_t A,
                  int32_t seq_first, float dropout_p, uint64_t seed, uint32_t dropout_stream, void* stream);
-/* delta_ws: fp32 workspace [B, A, S]; dqkv: bf16 [B*S, 3*A*64], fully overwritten */
+/* delta_ws: fp32 workspace [B, A, S]; dqkv: bf16 [B*S, 3*A*64], fully overwritten;
+ * dbias_qkv: fp32 [3*A*64] or NULL: += column sums of dqkv (the q/k/v bias gradients), must be zeroed by the caller */
 int dle_attn_bwd(const void* qkv, const float* mask, const void* ctx, const void* dctx, const float* lse,
-                 void* dqkv, float* delta_ws, int32_t B, int32_t S, int32_t A, int32_t seq_first, float dropout_p,
+                 void* dqkv, float* delta_ws, float* dbias_qkv, int32_t B, int32_t S, int32_t A, int32_t seq_first, float dropout_p,
                  uint64_t seed, uint32_t dropout_stream, void* stream);
 
 /* ------------------------------------------------------------------------------------------

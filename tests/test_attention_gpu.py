@@ -62,7 +62,10 @@ def test_attention_backward(B, S, A, ragged):
     g = torch.Generator(device="cuda").manual_seed(99)
     dctx = torch.randn(B * S, A * 64, generator=g, device="cuda").to(bf)
     ctx, lse = k.attn_fwd(qkv, mask, B, S, A)
-    dqkv = k.attn_bwd(qkv, mask, ctx, dctx, lse, B, S, A)
+    dbias = torch.zeros(3 * A * 64, device="cuda")
+    dqkv = k.attn_bwd(qkv, mask, ctx, dctx, lse, B, S, A, dbias=dbias)
+    # fused q/k/v bias gradients == column sums of the dqkv the kernel stored
+    torch.testing.assert_close(dbias, dqkv.float().sum(0), rtol=1e-3, atol=2e-2 * max(1.0, dqkv.float().abs().max().item()))
     x = qkv.float().requires_grad_(True)
     ctx_ref, _ = ref_attention(x, mask, B, S, A)
     ctx_ref.backward(dctx.float())

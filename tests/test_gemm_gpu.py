@@ -155,3 +155,16 @@ def test_invalid_args_return_error():
         k.gemm(a, b)
     with pytest.raises(L.DleError):
         k.gemm(a.cpu(), b.cpu())
+
+
+def test_epilogue_column_sums_of_output():
+    """colsum_out: the GEMM accumulates column sums of its (bf16) output -- the bias gradient of the producing layer -- so no
+    separate pass re-reads the tensor (warp transpose-reduce + red.global.add)."""
+    k, L = _k()
+    a, w, u = _rand((1000, 512), seed=40), _rand((512, 768), 0.05, seed=41), _rand((1000, 768), 1.5, seed=42)
+    acc = torch.zeros(768, device="cuda")
+    out = k.gemm(a, w, b_layout=L.LAYOUT_MN, epilogue=L.EPI_DGELU, aux=u, colsum_out=acc)
+    torch.testing.assert_close(acc, out.float().sum(0), rtol=1e-4, atol=2e-2)
+    acc2 = torch.zeros(768, device="cuda")
+    out2 = k.gemm(a, w, b_layout=L.LAYOUT_MN, colsum_out=acc2)
+    torch.testing.assert_close(acc2, out2.float().sum(0), rtol=1e-4, atol=2e-2)
