@@ -36,7 +36,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--seq", type=int, default=512, help="512 = phase 2 (headline), 128 = phase 1")
-    ap.add_argument("--batch", type=int, default=0, help="per-GPU micro-batch (0 = 64 @512, 256 @128: SURVEY.md 8d ranges)")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU micro-batch (0 = 128 @512, 512 @128 -- 65536 tokens per GPU per step; the reference ran 32 @512 / 256 @128 on 80 GB "
+                         "A100s, SURVEY.md 8d; 180 GB fits 4x that and the LAMB / allreduce cost per sequence halves again vs 64)")
     ap.add_argument("--max-pred", type=int, default=0)
     ap.add_argument("--no-dropout", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -163,7 +164,7 @@ def cpu_reference_run(cfg, S, P, ref_batch, steps, warmup):
 def workload(args):
     from deeplearningexamples_b200 import training as T
     S = args.seq
-    B = args.batch or (64 if S >= 384 else 256)
+    B = args.batch or (128 if S >= 384 else 512)
     P = args.max_pred or (80 if S >= 384 else 20)
     cfg = dict(T.BERT_LARGE)
     cfg["vocab_size"] = 30528                     # 30522 padded to a multiple of 8 (run_pretraining.py:383-384)
@@ -299,7 +300,9 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
     if os.path.exists(tpath):                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
         tj = json.load(open(tpath))
-        traffic, traffic_src = tj["avg_dram_traffic_bytes_per_launch"], "profiles/r01_gemm_traffic.json (ncu --set full, 12 forward GEMM launches of this command)"
+        traffic, traffic_src = tj["avg_dram_traffic_bytes_per_launch"], (
+            "profiles/r01_gemm_traffic.json (ncu --set full, 12 forward GEMM launches of this command; the same 12 launches move "
+            f"{tj.get('avg_algorithmic_bytes_per_launch', 0)} algorithmic bytes on average -- algorithmic_bytes_per_launch_avg below averages ALL timed launches)")
     gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof)
     gemm_flops = sum(f for _, _, f, _ in prof)
     ach = gemm_flops / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
@@ -309,7 +312,7 @@ def run_ours(args):
             "dtype": "bf16", "data": "synthetic", "config": config_dict(args, cfg, S, B, P, n),
             "e2e": {"value": round(e2e, 2), "unit": "sequences/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": round(ms_e2e / args.steps, 3)},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "hbm_peak_gb": round(torch.cuda.max_memory_allocated() / 2**30, 1),
             "roofline": {"kernel": "gemm_bf16_tcgen05_kernel (all dense projections/FFN, fwd+dgrad+wgrad)", "bound": "tensor",
                          "achieved": round(ach, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": round(ach / pk["tf_sustained"], 4),
                          "peak_source": pk["source"] + " (bf16_tflops_sustained: kernel timed inside a long step)",
