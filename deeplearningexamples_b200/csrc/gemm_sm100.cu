@@ -30,7 +30,9 @@ template <int BN> struct GemmCfg {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (BN == 256) ? 4 : 6;
     static constexpr int TMEM_COLS = 2 * BN;            // double-buffered accumulator
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 8 * 2560 /*epilogue staging*/ + 1024 /*align slack*/ + 256 /*barriers*/;
+    // epilogue: per warp a 2 KB output staging tile + a 2 KB cp.async landing tile for the residual / pre-activation operand,
+    // plus 3 x 2 x 256 B of bias staging (triple-buffered per tile, one slice per column half)
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 8 * 2048 + 8 * 2048 + 1536 + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct GemmKernelParams {
@@ -53,15 +55,20 @@ struct GemmKernelParams {
 // ----------------------------------------------------------------------------------------------
 // epilogue.  A TMEM load hands every thread 32 consecutive columns of ITS OWN row, so a direct 16-byte global
 // access per thread would touch 32 different 128-byte lines per warp instruction (measured: the bias+GELU epilogue
-// with two outputs ran at 53 % of peak, dropout+residual at 49 %).  Each epilogue warp therefore owns a 32 x 80 B
-// staging buffer (64 B of payload per row, padded to 80 B so both access patterns are bank-conflict free):
-//   store:  lane writes its row (4 x STS.128) -> __syncwarp -> lanes re-read as (row = it*8 + lane/4, chunk = lane%4)
-//           -> each ST.GLOBAL.128 covers 8 rows x 64 contiguous bytes
-//   load :  the mirror image for the residual / pre-activation operand.
-// fp32 outputs (split-K atomics, logits) keep the direct path.
+// with two outputs ran at 53 % of peak, dropout+residual at 49 %).  Each epilogue warp therefore owns two 32 x 64 B
+// tiles in shared memory, 16-byte units XOR-swizzled by (row >> 1) & 3 so that both access patterns are conflict-free:
+//   out tile:  lane writes its row (4 x STS.128) -> __syncwarp -> lanes re-read as (row = it*8 + lane/4, unit = lane%4)
+//              -> each ST.GLOBAL.128 covers 8 rows x 64 contiguous bytes
+//   aux tile:  the residual / pre-activation operand of the NEXT chunk lands here by cp.async (row-contiguous, no registers)
+//              while the current chunk is computed and stored; ncu showed 27 % of the dropout+residual epilogue's samples
+//              waiting on that load when it was issued in line.
+// The bias slice of the tile is staged once per tile (before the accumulator wait) instead of re-read from global per
+// chunk (8.5 % of the bias+GELU epilogue's samples).  fp32 outputs (split-K atomics, logits) keep the direct path.
 // ----------------------------------------------------------------------------------------------
-constexpr int EPI_STAGE_ROW = 80;                       // bytes
-constexpr int EPI_STAGE_BYTES = 32 * EPI_STAGE_ROW;     // per epilogue warp
+constexpr int EPI_TILE_BYTES = 32 * 64;                 // per epilogue warp, out and aux each
+constexpr int EPI_BIAS_BYTES = 3 * 2 * 256;             // [tile % 3][column half][<=128 bf16]
+
+__device__ __forceinline__ uint32_t epi_off(int row, int unit) { return (uint32_t)(row * 64 + ((unit ^ ((row >> 1) & 3)) << 4)); }
 
 __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
     uint4 r;
@@ -71,28 +78,26 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// rows [row_base, row_base+32) x cols [col0, col0+32) of a bf16 matrix -> this lane's row as 32 floats
-__device__ __forceinline__ void warp_load_rows(const bf16* __restrict__ src, long long ld, long long row_base, int col0, int M, int N,
-                                               uint32_t stage, int lane, float (&out)[32]) {
+// start the copy of rows [row_base, +32) x cols [col0, +32) of the bf16 aux matrix into this warp's aux tile
+__device__ __forceinline__ void aux_prefetch(const GemmKernelParams& p, long long row_base, int col0, uint32_t aux_tile, int lane) {
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
         const int rr = it * 8 + (lane >> 2), cc = lane & 3;
         const long long grow = row_base + rr; const int gcol = col0 + cc * 8;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (grow < M && gcol < N) v = ld_global_nc_v4(src + grow * ld + gcol);
-        sts_v4(stage + rr * EPI_STAGE_ROW + cc * 16, v.x, v.y, v.z, v.w);
+        if (grow < p.M && gcol < p.N) cp_async_16(aux_tile + epi_off(rr, cc), p.aux + grow * p.ld_aux + gcol);
     }
+}
+// this lane's row of the landed aux tile, still packed (4 x 8 bf16)
+__device__ __forceinline__ void aux_take(uint32_t aux_tile, int lane, uint4 (&a)[4]) {
+    cp_async_wait_all();
     __syncwarp();
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const uint4 v = lds_v4(stage + lane * EPI_STAGE_ROW + c * 16);
-        float2 f;
-        f = unpack_bf16(v.x); out[c * 8 + 0] = f.x; out[c * 8 + 1] = f.y;
-        f = unpack_bf16(v.y); out[c * 8 + 2] = f.x; out[c * 8 + 3] = f.y;
-        f = unpack_bf16(v.z); out[c * 8 + 4] = f.x; out[c * 8 + 5] = f.y;
-        f = unpack_bf16(v.w); out[c * 8 + 6] = f.x; out[c * 8 + 7] = f.y;
-    }
+    for (int c = 0; c < 4; ++c) a[c] = lds_v4(aux_tile + epi_off(lane, c));
     __syncwarp();
 }
 // this lane's row (32 floats) -> bf16 rows [row_base, +32) x cols [col0, +32) of dst, row-contiguous global stores
@@ -100,26 +105,41 @@ __device__ __forceinline__ void warp_store_rows(bf16* __restrict__ dst, long lon
                                                 uint32_t stage, int lane, const float (&v)[32]) {
 #pragma unroll
     for (int c = 0; c < 4; ++c)
-        sts_v4(stage + lane * EPI_STAGE_ROW + c * 16, pack_bf16(v[c * 8], v[c * 8 + 1]), pack_bf16(v[c * 8 + 2], v[c * 8 + 3]),
+        sts_v4(stage + epi_off(lane, c), pack_bf16(v[c * 8], v[c * 8 + 1]), pack_bf16(v[c * 8 + 2], v[c * 8 + 3]),
                pack_bf16(v[c * 8 + 4], v[c * 8 + 5]), pack_bf16(v[c * 8 + 6], v[c * 8 + 7]));
     __syncwarp();
+    uint4 w[4];                                  // all four shared loads first: the asm statements keep program order, and a load
+#pragma unroll                                   // immediately followed by its store exposes the shared-memory latency four times
+    for (int it = 0; it < 4; ++it) w[it] = lds_v4(stage + epi_off(it * 8 + (lane >> 2), lane & 3));
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
         const int rr = it * 8 + (lane >> 2), cc = lane & 3;
         const long long grow = row_base + rr; const int gcol = col0 + cc * 8;
-        const uint4 w = lds_v4(stage + rr * EPI_STAGE_ROW + cc * 16);
-        if (grow < M && gcol < N) st_global_v4(dst + grow * ld + gcol, w.x, w.y, w.z, w.w);
+        if (grow < M && gcol < N) st_global_v4(dst + grow * ld + gcol, w[it].x, w[it].y, w[it].z, w[it].w);
     }
     __syncwarp();
 }
+__device__ __forceinline__ void unpack8(const uint4& w, float* o) {
+    float2 f;
+    f = unpack_bf16(w.x); o[0] = f.x; o[1] = f.y;
+    f = unpack_bf16(w.y); o[2] = f.x; o[3] = f.y;
+    f = unpack_bf16(w.z); o[4] = f.x; o[5] = f.y;
+    f = unpack_bf16(w.w); o[6] = f.x; o[7] = f.y;
+}
 
-// one 32-row x 32-column chunk of one epilogue warp; `row` = this lane's row, row_base = first row of the warp
-__device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const uint32_t (&acc)[32], long long row_base, int lane,
-                                               int col0, uint32_t stage) {
+// one 32-row x 32-column chunk of one epilogue warp; `row` = this lane's row, row_base = first row of the warp.
+// bias_s = shared address of this chunk's 32 staged bias values; aux = this lane's row of the aux operand (packed bf16).
+__device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const uint32_t (&acc)[32], const uint4 (&aux)[4], long long row_base,
+                                               int lane, int col0, uint32_t stage, uint32_t bias_s) {
     const long long row = row_base + lane;
     float v[32];
+    if (p.alpha != 1.0f) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) * p.alpha;
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]) * p.alpha;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+    }
     const int ncols = min(32, p.N - col0);      // multiple of 8 (N % 8 == 0 is enforced); <= 0 for an out-of-range chunk
     if (ncols <= 0) return;                      // warp-uniform
 
@@ -132,17 +152,16 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
         }
         return;
     }
-    if (p.bias != nullptr) {
+    if (p.bias != nullptr) {                     // staged slice is zero-filled beyond N
+        uint4 bw[4];
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-            if (i < ncols) {
-                uint4 b = *reinterpret_cast<const uint4*>(p.bias + col0 + i);
-                float2 f;
-                f = unpack_bf16(b.x); v[i] += f.x; v[i + 1] += f.y;
-                f = unpack_bf16(b.y); v[i + 2] += f.x; v[i + 3] += f.y;
-                f = unpack_bf16(b.z); v[i + 4] += f.x; v[i + 5] += f.y;
-                f = unpack_bf16(b.w); v[i + 6] += f.x; v[i + 7] += f.y;
-            }
+        for (int i = 0; i < 4; ++i) bw[i] = lds_v4(bias_s + i * 16);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float b[8];
+            unpack8(bw[i], b);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[i * 8 + k] += b[k];
         }
     }
     if (p.epilogue == DLE_EPI_F32) {
@@ -167,21 +186,30 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
             for (int i = 0; i < 32; ++i) v[i] = ((keep >> i) & 1u) ? v[i] * p.drop_scale : 0.f;
         }
         if (p.aux != nullptr) {
-            float a[32];
-            warp_load_rows(p.aux, p.ld_aux, row_base, col0, p.M, p.N, stage, lane, a);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += a[i];
+            for (int c = 0; c < 4; ++c) {
+                float a[8];
+                unpack8(aux[c], a);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[c * 8 + k] += a[k];
+            }
         }
     } else if (p.epilogue == DLE_EPI_DGELU) {
-        float a[32];                                        // stored pre-activation u
-        warp_load_rows(p.aux, p.ld_aux, row_base, col0, p.M, p.N, stage, lane, a);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] *= gelu_tanh_grad(a[i]);
+        for (int c = 0; c < 4; ++c) {
+            float a[8];                                     // stored pre-activation u
+            unpack8(aux[c], a);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[c * 8 + k] *= gelu_tanh_grad(a[k]);
+        }
     } else if (p.epilogue == DLE_EPI_ADD) {
-        float a[32];
-        warp_load_rows(p.aux, p.ld_aux, row_base, col0, p.M, p.N, stage, lane, a);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += a[i];
+        for (int c = 0; c < 4; ++c) {
+            float a[8];
+            unpack8(aux[c], a);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[c * 8 + k] += a[k];
+        }
     } else if (p.epilogue == DLE_EPI_BIAS_TANH) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = tanhf(v[i]);
@@ -205,8 +233,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     using Cfg = GemmCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* epi_stage = smem + Cfg::STAGES * Cfg::STAGE_BYTES;                 // 8 warps x EPI_STAGE_BYTES
-    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + 8 * EPI_STAGE_BYTES);
+    uint8_t* epi_stage = smem + Cfg::STAGES * Cfg::STAGE_BYTES;                 // 8 warps x (out tile, aux tile), then the bias slices
+    uint8_t* epi_bias = epi_stage + 16 * EPI_TILE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(epi_bias + EPI_BIAS_BYTES);
     uint64_t* full_bar = bars;                         // [STAGES]  TMA -> MMA
     uint64_t* empty_bar = bars + Cfg::STAGES;          // [STAGES]  MMA -> TMA
     uint64_t* tmem_full = bars + 2 * Cfg::STAGES;      // [2]       MMA -> epilogue
@@ -301,26 +330,79 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         // ===================== epilogue warps (TMEM -> registers -> global) =====================
         const int q = warp & 3;                          // TMEM lane quarter this warp may access
         const int half = (warp - 4) >> 2;                // two warps share a quarter: each drains half the columns
+        constexpr int CH = BN / 64;                      // chunks per warp per tile
+        const uint32_t out_tile = smem_u32(epi_stage) + (warp - 4) * 2 * EPI_TILE_BYTES;
+        const uint32_t aux_tile = out_tile + EPI_TILE_BYTES;
+        const bool use_aux = p.aux != nullptr && (p.epilogue == DLE_EPI_BIAS_DROPOUT_RESIDUAL || p.epilogue == DLE_EPI_DGELU ||
+                                                  p.epilogue == DLE_EPI_ADD);
+        if (use_aux && (int)blockIdx.x < total_units) {  // operand of the very first chunk
+            const int tile = blockIdx.x / p.splits;
+            const int m_blk = tile / p.n_tiles, n_blk = tile - m_blk * p.n_tiles;
+            aux_prefetch(p, (long long)m_blk * BM + q * 32, n_blk * BN + half * (BN / 2), aux_tile, lane);
+        }
         int it = 0;
         for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
             const int tile = unit / p.splits;
             const int m_blk = tile / p.n_tiles, n_blk = tile - m_blk * p.n_tiles;
             const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
+            // bias slice of this warp's column half -> shared.  The slice of tile it+1 is fetched into two registers at the top of tile it
+            // and stored after its last chunk, so the global latency never sits in front of the accumulator (in the epilogue-bound
+            // regime the accumulator is already waiting).  The four warps of a half write the same values into the same slice; slices
+            // rotate over three tiles because a warp can run at most one tile ahead of a sibling (tmem_empty needs all eight arrivals).
+            const uint32_t bias_s = smem_u32(epi_bias) + ((it % 3) * 2 + half) * 256;
+            const uint32_t bias_next = smem_u32(epi_bias) + (((it + 1) % 3) * 2 + half) * 256;
+            uint2 bnext = make_uint2(0u, 0u);
+            const bool has_next = p.bias != nullptr && unit + (int)gridDim.x < total_units;
+            if (p.bias != nullptr) {
+                if (it == 0) {
+                    uint2 b0 = make_uint2(0u, 0u);
+                    const int col = n_blk * BN + half * (BN / 2) + lane * (BN / 64);
+                    if (col < p.N) { if constexpr (BN == 256) b0 = *reinterpret_cast<const uint2*>(p.bias + col); else b0.x = *reinterpret_cast<const uint32_t*>(p.bias + col); }
+                    if constexpr (BN == 256) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(bias_s + lane * 8), "r"(b0.x), "r"(b0.y) : "memory");
+                    else asm volatile("st.shared.b32 [%0], %1;" ::"r"(bias_s + lane * 4), "r"(b0.x) : "memory");
+                    __syncwarp();
+                }
+                if (has_next) {
+                    const int tile2 = (unit + (int)gridDim.x) / p.splits;
+                    const int n2 = tile2 - (tile2 / p.n_tiles) * p.n_tiles;
+                    const int col = n2 * BN + half * (BN / 2) + lane * (BN / 64);
+                    if (col < p.N) { if constexpr (BN == 256) bnext = *reinterpret_cast<const uint2*>(p.bias + col); else bnext.x = *reinterpret_cast<const uint32_t*>(p.bias + col); }
+                }
+            }
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const long long row_base = (long long)m_blk * BM + q * 32;
-            const uint32_t stage_addr = smem_u32(epi_stage) + (warp - 4) * EPI_STAGE_BYTES;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-            for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
+            for (int cl = 0; cl < CH; ++cl) {
+                const int c = half * CH + cl;
                 uint32_t r[32];
                 tmem_ld32(taddr + c * 32, r);
+                uint4 a[4];
+                if (use_aux) {
+                    aux_take(aux_tile, lane, a);             // landed while the previous chunk was computed / stored
+                    if (cl + 1 < CH) {
+                        aux_prefetch(p, row_base, n_blk * BN + (c + 1) * 32, aux_tile, lane);
+                    } else if (unit + (int)gridDim.x < total_units) {
+                        const int tile2 = (unit + (int)gridDim.x) / p.splits;
+                        const int m2 = tile2 / p.n_tiles, n2 = tile2 - m2 * p.n_tiles;
+                        aux_prefetch(p, (long long)m2 * BM + q * 32, n2 * BN + half * (BN / 2), aux_tile, lane);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) a[k] = make_uint4(0u, 0u, 0u, 0u);
+                }
                 tmem_ld_wait();
-                if (row_base < p.M) epilogue_chunk(p, r, row_base, lane, n_blk * BN + c * 32, stage_addr);
+                if (row_base < p.M) epilogue_chunk(p, r, a, row_base, lane, n_blk * BN + c * 32, out_tile, bias_s + cl * 64);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);    // one arrival per epilogue warp
+            if (has_next) {
+                if constexpr (BN == 256) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(bias_next + lane * 8), "r"(bnext.x), "r"(bnext.y) : "memory");
+                else asm volatile("st.shared.b32 [%0], %1;" ::"r"(bias_next + lane * 4), "r"(bnext.x) : "memory");
+                __syncwarp();
+            }
         }
     }
 

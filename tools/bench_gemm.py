@@ -57,16 +57,27 @@ def main():
         cases.append((f"fwd ffn2 +drop+res tile_n={tn or 256}", lambda tn=tn: k.gemm(xi, w_2, bias=b_i[:H], aux=x, epilogue=L.EPI_BIAS_DROPOUT_RESIDUAL, dropout_p=0.1, seed=1, tile_n=tn), None, 2 * T * H * I))
         cases.append((f"dgrad ffn1 tile_n={tn or 256}", lambda tn=tn: k.gemm(xi, w_1, b_layout=L.LAYOUT_MN, tile_n=tn), None, 2 * T * H * I))
         cases.append((f"dgrad out tile_n={tn or 256}", lambda tn=tn: k.gemm(x, w_o, b_layout=L.LAYOUT_MN, tile_n=tn), None, 2 * T * H * H))
-    for splits in (1, 2, 4, 8):
+    u = torch.randn(T, I, device="cuda").to(bf)
+    cs = torch.zeros(I, device="cuda")
+    cases.append(("dgrad ffn2 *gelu'(u) +colsum", lambda: k.gemm(x, w_2, b_layout=L.LAYOUT_MN, aux=u, epilogue=L.EPI_DGELU, colsum_out=cs), None, 2 * T * H * I))
+    cases.append(("dgrad ffn1 +add", lambda: k.gemm(xi, w_1, b_layout=L.LAYOUT_MN, aux=x, epilogue=L.EPI_ADD), None, 2 * T * H * I))
+    cases.append(("dgrad qkv +add", lambda: k.gemm(dy3, w_qkv, b_layout=L.LAYOUT_MN, aux=x, epilogue=L.EPI_ADD), None, 2 * T * H * 3 * H))
+    only = os.environ.get("CASES", "")
+    if only == "epi":          # the epilogue-heavy subset (A/B runs of epilogue changes)
+        cases = [c for c in cases if any(t in c[0] for t in ("gelu", "drop+res tile_n=256", "+add", "fwd qkv", "fwd out  "))]
+    for splits in ((1, 2, 4, 8) if only != "epi" else ()):
         cases.append((f"wgrad ffn1 dy[T,I]^T·x[T,H] splits={splits}",
                       lambda s=splits: k.gemm(xi, x, a_layout=L.LAYOUT_MN, b_layout=L.LAYOUT_MN, epilogue=L.EPI_ATOMIC_F32, splits=s,
                                               out=torch.zeros(I, H, device="cuda")),
                       (lambda: xi.t() @ x) if splits == 1 else None, 2 * T * H * I))
-    for splits in (1, 4, 8, 16):
+    for splits in ((1, 4, 8, 16) if only != "epi" else ()):
         cases.append((f"wgrad out dy[T,H]^T·x[T,H] splits={splits}",
                       lambda s=splits: k.gemm(x, x, a_layout=L.LAYOUT_MN, b_layout=L.LAYOUT_MN, epilogue=L.EPI_ATOMIC_F32, splits=s,
                                               out=torch.zeros(H, H, device="cuda")),
                       (lambda: x.t() @ x) if splits == 1 else None, 2 * T * H * H))
+    exact = os.environ.get("ONLY", "")
+    if exact:                  # one case, e.g. under ncu
+        cases = [c for c in cases if c[0] == exact]
     for name, ours, ref, flops in cases:
         ms = timeit(ours)
         ms_ref = timeit(ref) if ref is not None else float("nan")
