@@ -458,7 +458,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         const long long bh = (long long)b * p.A + h;
         const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS);
         for (int j = 0; j < n; ++j) {
-            const float* mk = sMask + j * TQ + qc * 32;
+            // my 32 key columns of this kv tile: additive mask (already x log2e) from shared memory, skipped entirely when it is all
+            // zero (warp-uniform; unpadded batches).  Explicit ld.shared: the generic loads the compiler emitted for sMask[] went
+            // through the global/local queue (ncu: 4 % of the kernel's samples on `lg` throttle at those eight loads).
+            const uint32_t mk_addr = smem_u32(sMask + j * TQ + qc * 32);
+            const bool masked = __any_sync(0xffffffffu, sMask[j * TQ + qc * 32 + lane] != 0.f);
             for (int i = 0; i < n; ++i) {
                 const int t = j * n + i;
                 const float lse2 = p.lse[bh * S + i * TQ + r] * LOG2E;
@@ -474,8 +478,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
                     tmem_ld32(tmem_SP + lane_addr + qc * 32, v);
                     tmem_ld_wait();
                     float e[32];
+                    if (masked) {
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) e[k] = ex2(fmaf(__uint_as_float(v[k]), p.scale_log2, mk[k]) - lse2);
+                        for (int g = 0; g < 8; ++g) {
+                            float m0, m1, m2, m3;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(m0), "=f"(m1), "=f"(m2), "=f"(m3) : "r"(mk_addr + g * 16));
+                            e[4 * g + 0] = ex2(fmaf(__uint_as_float(v[4 * g + 0]), p.scale_log2, m0) - lse2);
+                            e[4 * g + 1] = ex2(fmaf(__uint_as_float(v[4 * g + 1]), p.scale_log2, m1) - lse2);
+                            e[4 * g + 2] = ex2(fmaf(__uint_as_float(v[4 * g + 2]), p.scale_log2, m2) - lse2);
+                            e[4 * g + 3] = ex2(fmaf(__uint_as_float(v[4 * g + 3]), p.scale_log2, m3) - lse2);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) e[k] = ex2(fmaf(__uint_as_float(v[k]), p.scale_log2, -lse2));
+                    }
 #pragma unroll
                     for (int k = 0; k < 16; ++k) pk[k] = pack_bf16(e[2 * k], e[2 * k + 1]);
                     if (p.drop_thresh != 0u) {
