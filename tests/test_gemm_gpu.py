@@ -168,3 +168,29 @@ def test_epilogue_column_sums_of_output():
     acc2 = torch.zeros(768, device="cuda")
     out2 = k.gemm(a, w, b_layout=L.LAYOUT_MN, colsum_out=acc2)
     torch.testing.assert_close(acc2, out2.float().sum(0), rtol=1e-4, atol=2e-2)
+
+
+@pytest.mark.parametrize("N,tile_n", [(1024, 0), (512, 128)])
+def test_epilogues_many_tiles_per_cta(N, tile_n):
+    """Persistent-kernel state that only shows with several tiles per CTA (the encoder shapes run 14+): the bias slice is staged one
+    tile ahead and rotates over three shared-memory slots, and the residual / pre-activation operand of a tile's first chunk is
+    prefetched by cp.async from the previous tile's last chunk.  16384 x N output = 512 tiles on 148 CTAs, non-zero bias that differs
+    per column tile, every epilogue that takes a bias or an aux operand, against fp32 torch."""
+    k, L = _k()
+    M, K = 16384, 256
+    a, w = _rand((M, K), seed=40), _rand((N, K), 0.1, seed=41)
+    bias = (_rand((N,), 1.0, seed=42).float() + torch.arange(N, device="cuda").float() / N).to(torch.bfloat16)
+    res = _rand((M, N), 1.0, seed=43)
+    base = a.float() @ w.float().t()
+    _close(k.gemm(a, w, bias=bias, tile_n=tile_n), base + bias.float())
+    _close(k.gemm(a, w, bias=bias, aux=res, epilogue=L.EPI_BIAS_DROPOUT_RESIDUAL, dropout_p=0.0, tile_n=tile_n), base + bias.float() + res.float())
+    g, u = k.gemm(a, w, bias=bias, epilogue=L.EPI_BIAS_GELU, tile_n=tile_n)
+    _close(u, base + bias.float())
+    _close(g, torch.nn.functional.gelu(u.float(), approximate="tanh"), rtol=1e-2, atol=1e-2)
+    _close(k.gemm(a, w, aux=res, epilogue=L.EPI_ADD, tile_n=tile_n), base + res.float())
+    cs = torch.zeros(N, device="cuda")
+    out = k.gemm(a, w, aux=res, epilogue=L.EPI_DGELU, colsum_out=cs, tile_n=tile_n)
+    rf = res.float().requires_grad_(True)
+    torch.nn.functional.gelu(rf, approximate="tanh").sum().backward()
+    _close(out, base * rf.grad)
+    torch.testing.assert_close(cs, out.float().sum(dim=0), rtol=1e-3, atol=1e-2 * out.float().abs().sum(dim=0).max().item())
