@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdle_b200.so")
+# DLE_LIB_PATH: load another build of the SAME ABI (same-box A/B measurements of two kernel versions); default = the in-tree build
+LIB_PATH = os.environ.get("DLE_LIB_PATH") or os.path.join(_HERE, "libdle_b200.so")
 
 DLE_DTYPE_F32, DLE_DTYPE_BF16 = 0, 1
 LAYOUT_K, LAYOUT_MN = 0, 1
@@ -23,7 +24,7 @@ class GemmArgs(ctypes.Structure):
                 ("M", _i32), ("N", _i32), ("K", _i32), ("a_layout", _i32), ("b_layout", _i32),
                 ("lda", _i64), ("ldb", _i64), ("ldo", _i64), ("ldo2", _i64), ("ld_aux", _i64),
                 ("epilogue", _i32), ("splits", _i32), ("tile_n", _i32), ("alpha", _f32),
-                ("dropout_p", _f32), ("dropout_stream", _u32), ("seed", _u64), ("colsum_out", _vp)]
+                ("dropout_p", _f32), ("dropout_stream", _u32), ("seed", _u64), ("seed_dev", _vp), ("colsum_out", _vp)]
 
 
 class LambTensor(ctypes.Structure):
@@ -40,12 +41,12 @@ class LambGroup(ctypes.Structure):
 SIGNATURES = {
     "dle_version": (_i32, [ctypes.c_char_p, _i32]),
     "dle_gemm_bf16": (_i32, [ctypes.POINTER(GemmArgs), _vp]),
-    "dle_attn_fwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _u64, _u32, _vp]),
-    "dle_attn_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _u64, _u32, _vp]),
-    "dle_add_ln_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _u64, _u32, _vp]),
+    "dle_attn_fwd": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _u64, _vp, _u32, _vp]),
+    "dle_attn_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _u64, _vp, _u32, _vp]),
+    "dle_add_ln_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _u64, _vp, _u32, _vp]),
     "dle_ln_bwd_partials": (_i32, [_i64]),
     "dle_ln_bwd_partials_h": (_i32, [_i64, _i32]),
-    "dle_add_ln_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _u64, _u32, _vp]),
+    "dle_add_ln_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _u64, _vp, _u32, _vp]),
     "dle_colsum_finalize": (_i32, [_vp, _i32, _i32, _vp, _i32, _i32, _vp]),
     "dle_colsum_finalize_batched": (_i32, [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _vp]),
     "dle_colsum_partials": (_i32, [_i64]),
@@ -53,11 +54,12 @@ SIGNATURES = {
     "dle_bias_gelu_fwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "dle_bias_gelu_bwd": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp]),
     "dle_embed_ln_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32,
-                                _i32, _f32, _f32, _u64, _u32, _vp, _vp]),
+                                _i32, _f32, _f32, _u64, _vp, _u32, _vp, _vp]),
     "dle_embed_ln_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32,
-                                _u64, _u32, _vp]),
+                                _u64, _vp, _u32, _vp]),
     "dle_gather_rows": (_i32, [_vp, _vp, _vp, _i64, _i32, _i64, _vp, _vp]),
     "dle_scatter_rows": (_i32, [_vp, _vp, _vp, _i64, _i32, _i64, _vp]),
+    "dle_advance_u64": (_i32, [_vp, _u64, _vp]),
     "dle_cast_f32_to_bf16": (_i32, [_vp, _vp, _i64, _vp]),
     "dle_cast_bf16_to_f32": (_i32, [_vp, _vp, _i64, _vp]),
     "dle_lamb_plan_create": (_i32, [ctypes.POINTER(LambTensor), _i32, ctypes.POINTER(LambGroup), _i32, _i32,

@@ -126,10 +126,101 @@ __device__ __forceinline__ uint32_t dropout_keep32(uint64_t seed, uint32_t strea
     }
     return m;
 }
+// The same decisions for ONE byte of the group: bits [8*w, 8*w+8) of dropout_keep32(...), i.e. the keep bits of the 8 consecutive
+// elements starting at (group32 << 5) + 8*w.  For kernels whose threads own 8 elements (LayerNorm, embedding): the Philox block is
+// still needed in full, but only one of its four words is expanded (8 LCG steps instead of 32).
+template <int ROUNDS = 7>
+__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint32_t stream, uint64_t group32, int w, uint32_t thresh16) {
+    const uint4 r = philox4x32<ROUNDS>(make_uint4((uint32_t)group32, (uint32_t)(group32 >> 32), stream, 0x5eed32u),
+                                       make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint32_t t = thresh16 << 16;
+    uint32_t s = (w == 0) ? r.x : (w == 1) ? r.y : (w == 2) ? r.z : r.w;
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        m |= (s >= t ? 1u : 0u) << k;
+        s = s * 747796405u + 2891336453u;
+    }
+    return m;
+}
 __host__ __device__ __forceinline__ uint32_t dropout_thresh16(float p) {
     float t = p * 65536.0f + 0.5f;
     return t <= 0.f ? 0u : (t >= 65535.f ? 65535u : (uint32_t)t);
 }
+
+// ---------------------------------------------------------------------------------------------
+// dropout seeds under CUDA graphs: the host seed of a call site is frozen into a captured graph, so every dropout kernel also
+// takes an optional DEVICE counter (`seed_dev`, bumped once per training step by dle_advance_u64); the effective seed is
+// seed + *seed_dev * golden-ratio constant.  Forward and backward of one step read the same counter value.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long effective_seed(unsigned long long seed, const unsigned long long* seed_dev) {
+    return seed_dev ? seed + __ldg(seed_dev) * 0x9E3779B97F4A7C15ull : seed;
+}
+
+// ---------------------------------------------------------------------------------------------
+// packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2 / FMUL2: one issue slot for two lanes of work) and byte permute
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pack_f32x2(a0, a1)), "l"(pack_f32x2(b0, b1)), "l"(pack_f32x2(c0, c1)));
+    unpack_f32x2(d, d0, d1);
+}
+__device__ __forceinline__ void fmul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pack_f32x2(a0, a1)), "l"(pack_f32x2(b0, b1)));
+    unpack_f32x2(d, d0, d1);
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pack_f32x2(a0, a1)), "l"(pack_f32x2(b0, b1)));
+    unpack_f32x2(d, d0, d1);
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Attention-probability dropout (forward and backward of the fused attention kernels): keep decisions for the 32 consecutive
+// elements of group `group32`, delivered as 16 AND-masks for packed bf16x2 pairs (mask[i] covers elements 2i | 2i+1: 0xFFFF per kept
+// half) -- P~ = P & mask costs one LOP3 per pair instead of a bit extract + select per element.
+//   one Philox4x32-7 call -> four keyed words r_w; each is spread over four pair-words by an odd multiplier (bijective) and an
+//   xor-shift (x ^ x>>16: both halfwords of the result are uniform and jointly independent); a halfword keeps its element iff its low
+//   15 bits are >= t15 = round(p * 32768): (h & 0x7FFF) + (0x8000 - t15) sets bit 15 exactly then, and PRMT with sign replication
+//   turns bits 15 / 31 into 0xFFFF / 0xFFFF0000.  p is therefore quantised to 1/32768; `dropout_thresh15` and the 1/(1-p) scale must
+//   use the same quantised value (attn_drop_params).
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t dropout_thresh15(float p) {
+    float t = p * 32768.0f + 0.5f;
+    return t <= 0.f ? 0u : (t >= 32767.f ? 32767u : (uint32_t)t);
+}
+template <int ROUNDS = 7>
+__device__ __forceinline__ void attn_dropout_masks16(unsigned long long seed, uint32_t stream, unsigned long long group32, uint32_t k2,
+                                                     uint32_t (&mask)[16]) {
+    const uint4 r = philox4x32<ROUNDS>(make_uint4((uint32_t)group32, (uint32_t)(group32 >> 32), stream, 0xa77d20u),
+                                       make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint32_t x[4] = {r.x, r.y, r.z, r.w};
+    const uint32_t C[4] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu};
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t m = x[w] * C[k];
+            const uint32_t y = ((m ^ (m >> 16)) & 0x7FFF7FFFu) + k2;
+            mask[w * 4 + k] = prmt(y, 0u, 0xBB99u);
+        }
+    }
+}
+__host__ __device__ __forceinline__ uint32_t attn_dropout_k2(uint32_t thresh15) { return (0x8000u - thresh15) * 0x00010001u; }
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier
@@ -147,17 +238,30 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // thread until the phase flips instead of returning after the (short) default limit: ncu showed ~30 % of all executed warp
 // instructions of the attention kernels were TRYWAIT/BRA/YIELD iterations of single-lane producer / MMA-issuer waits, competing
 // for issue slots with the softmax warps of the same SM sub-partition.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t addr = smem_u32(bar);
+// Watchdog: a wait that has not completed after 4 s of wall clock (kernels here last milliseconds) is a protocol bug; trap so the
+// launch fails with an error instead of hanging the GPU.
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t addr, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
-        "@P1 bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
-        "}\n" ::"r"(addr), "r"(parity), "r"(0x989680u) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n" : "=r"(ok) : "r"(addr), "r"(parity), "r"(0x989680u) : "memory");
+    return ok;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    if (mbar_try_wait(addr, parity)) return;
+    const unsigned long long t0 = global_timer_ns();
+    while (!mbar_try_wait(addr, parity)) {
+        if (global_timer_ns() - t0 > 4000000000ull) __trap();
+    }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05 operand reads)

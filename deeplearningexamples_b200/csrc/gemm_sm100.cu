@@ -48,6 +48,7 @@ struct GemmKernelParams {
     uint32_t drop_thresh;  // 16-bit threshold, 0 = dropout off
     uint32_t drop_stream;
     unsigned long long seed;
+    const unsigned long long* seed_dev;
     float alpha;
     float* colsum_out;     // [N] fp32 or null: += column sums of the (bf16-rounded) output, e.g. the bias gradient of the layer below
 };
@@ -130,7 +131,7 @@ __device__ __forceinline__ void unpack8(const uint4& w, float* o) {
 // one 32-row x 32-column chunk of one epilogue warp; `row` = this lane's row, row_base = first row of the warp.
 // bias_s = shared address of this chunk's 32 staged bias values; aux = this lane's row of the aux operand (packed bf16).
 __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const uint32_t (&acc)[32], const uint4 (&aux)[4], long long row_base,
-                                               int lane, int col0, uint32_t stage, uint32_t bias_s) {
+                                               int lane, int col0, uint32_t stage, uint32_t bias_s, unsigned long long seed) {
     const long long row = row_base + lane;
     float v[32];
     if (p.alpha != 1.0f) {
@@ -181,7 +182,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
         for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(__bfloat162float(__float2bfloat16_rn(v[i])));
     } else if (p.epilogue == DLE_EPI_BIAS_DROPOUT_RESIDUAL) {
         if (p.drop_thresh != 0) {
-            const uint32_t keep = dropout_keep32(p.seed, p.drop_stream, (unsigned long long)(row * (long long)p.N + col0) >> 5, p.drop_thresh);
+            const uint32_t keep = dropout_keep32(seed, p.drop_stream, (unsigned long long)(row * (long long)p.N + col0) >> 5, p.drop_thresh);
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = ((keep >> i) & 1u) ? v[i] * p.drop_scale : 0.f;
         }
@@ -333,6 +334,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         constexpr int CH = BN / 64;                      // chunks per warp per tile
         const uint32_t out_tile = smem_u32(epi_stage) + (warp - 4) * 2 * EPI_TILE_BYTES;
         const uint32_t aux_tile = out_tile + EPI_TILE_BYTES;
+        const unsigned long long seed = (p.drop_thresh != 0u) ? effective_seed(p.seed, p.seed_dev) : 0ull;
         const bool use_aux = p.aux != nullptr && (p.epilogue == DLE_EPI_BIAS_DROPOUT_RESIDUAL || p.epilogue == DLE_EPI_DGELU ||
                                                   p.epilogue == DLE_EPI_ADD);
         if (use_aux && (int)blockIdx.x < total_units) {  // operand of the very first chunk
@@ -393,7 +395,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     for (int k = 0; k < 4; ++k) a[k] = make_uint4(0u, 0u, 0u, 0u);
                 }
                 tmem_ld_wait();
-                if (row_base < p.M) epilogue_chunk(p, r, a, row_base, lane, n_blk * BN + c * 32, out_tile, bias_s + cl * 64);
+                if (row_base < p.M) epilogue_chunk(p, r, a, row_base, lane, n_blk * BN + c * 32, out_tile, bias_s + cl * 64, seed);
             }
             tc_fence_before();
             __syncwarp();
@@ -486,6 +488,7 @@ static int launch_gemm(const dle_gemm_args* a, cudaStream_t stream) {
     p.drop_scale = (a->dropout_p > 0.f) ? 1.0f / (1.0f - a->dropout_p) : 1.0f;
     p.drop_stream = a->dropout_stream;
     p.seed = a->seed;
+    p.seed_dev = reinterpret_cast<const unsigned long long*>(a->seed_dev);
     p.alpha = a->alpha;
     p.colsum_out = reinterpret_cast<float*>(a->colsum_out);
 

@@ -43,8 +43,15 @@ struct LambPlan {                            // host-side handle
     void* block; size_t block_bytes;
     int n_tensors, n_groups, n_chunks, grad_dtype;
     long long total_numel;
-    void* host_stage = nullptr; long long* stage_numel = nullptr; cudaEvent_t stage_event = nullptr;
+    // pinned staging for dle_lamb_plan_update: a ring of LAMB_EAGER_SLOTS slots (one event each: a slot is rewritten only after the
+    // copy that read it has run) plus LAMB_CAPTURE_SLOTS slots that are handed out once each to updates issued under CUDA-graph
+    // capture (the captured copy node re-reads its slot on every replay, so such a slot is never reused).  Allocated at plan creation:
+    // nothing on the per-step path allocates or synchronises.
+    LambTensorDev* host_stage = nullptr; long long* stage_numel = nullptr;
+    cudaEvent_t stage_event[8] = {}; bool stage_used[8] = {};
+    int next_slot = 0, next_capture_slot = 0;
 };
+constexpr int LAMB_EAGER_SLOTS = 8, LAMB_CAPTURE_SLOTS = 4;
 
 __device__ __forceinline__ float block_reduce_sum(float v, float* sh) {
     v = warp_sum(v);
@@ -370,34 +377,50 @@ extern "C" int dle_lamb_plan_create(const dle_lamb_tensor* ht, int32_t n_tensors
     pl->psq = reinterpret_cast<double*>(d + o_p); pl->usq = reinterpret_cast<double*>(d + o_u);
     pl->block = dev; pl->block_bytes = bytes; pl->n_tensors = n_tensors; pl->n_groups = n_groups;
     pl->n_chunks = (int)n_chunks; pl->grad_dtype = grad_dtype; pl->total_numel = total;
+    pl->stage_numel = new long long[n_tensors];
+    for (int i = 0; i < n_tensors; ++i) pl->stage_numel[i] = ht[i].numel;
+    void* hs = nullptr;
+    if (cudaMallocHost(&hs, sizeof(LambTensorDev) * (size_t)n_tensors * (LAMB_EAGER_SLOTS + LAMB_CAPTURE_SLOTS)) != cudaSuccess) {
+        cudaFree(dev); delete[] pl->stage_numel; delete pl; return DLE_ERR_CUDA;
+    }
+    pl->host_stage = static_cast<LambTensorDev*>(hs);
+    for (int i = 0; i < LAMB_EAGER_SLOTS; ++i)
+        if (cudaEventCreateWithFlags(&pl->stage_event[i], cudaEventDisableTiming) != cudaSuccess) return DLE_ERR_CUDA;
     *plan_out = pl;
     return DLE_OK;
 }
 
 // Re-point an existing plan at new gradient / parameter addresses (same tensor count, sizes and groups): one small
-// H2D copy on `stream`, no allocation.  Autograd hands out fresh gradient tensors every step when the driver uses
+// H2D copy on `stream`, no allocation, no host synchronisation, legal under CUDA-graph capture.  Autograd hands out fresh gradient tensors every step when the driver uses
 // zero_grad(set_to_none=True) (run_pretraining.py:536), so this is on the per-step path.
 extern "C" int dle_lamb_plan_update(void* plan, const dle_lamb_tensor* ht, int32_t n_tensors, void* stream) {
     DLE_CHECK_ARG(plan && ht);
     LambPlan* pl = static_cast<LambPlan*>(plan);
     DLE_CHECK_ARG(n_tensors == pl->n_tensors);
-    if (pl->host_stage == nullptr) {
-        if (cudaMallocHost(&pl->host_stage, sizeof(LambTensorDev) * n_tensors) != cudaSuccess) return DLE_ERR_CUDA;
-        pl->stage_numel = new long long[n_tensors];
-        if (cudaMemcpy(pl->host_stage, pl->tensors, sizeof(LambTensorDev) * n_tensors, cudaMemcpyDeviceToHost) != cudaSuccess) return DLE_ERR_CUDA;
-        for (int i = 0; i < n_tensors; ++i) pl->stage_numel[i] = static_cast<LambTensorDev*>(pl->host_stage)[i].n;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cap) != cudaSuccess) return DLE_ERR_CUDA;
+    int slot;
+    if (cap == cudaStreamCaptureStatusActive) {
+        if (pl->next_capture_slot >= LAMB_CAPTURE_SLOTS) return DLE_ERR_NOSYS;      // more graph captures than reserved slots
+        slot = LAMB_EAGER_SLOTS + pl->next_capture_slot++;
+    } else {
+        slot = pl->next_slot;
+        pl->next_slot = (pl->next_slot + 1) % LAMB_EAGER_SLOTS;
+        // the slot was last read by the copy issued LAMB_EAGER_SLOTS updates ago: only a host running that far ahead ever waits here
+        if (pl->stage_used[slot] && cudaEventQuery(pl->stage_event[slot]) == cudaErrorNotReady &&
+            cudaEventSynchronize(pl->stage_event[slot]) != cudaSuccess) return DLE_ERR_CUDA;
     }
-    LambTensorDev* t = static_cast<LambTensorDev*>(pl->host_stage);
-    // the staging buffer may still be in flight from the previous update on this stream
-    if (pl->stage_event && cudaEventSynchronize(pl->stage_event) != cudaSuccess) return DLE_ERR_CUDA;
+    LambTensorDev* t = pl->host_stage + (size_t)slot * n_tensors;
     for (int i = 0; i < n_tensors; ++i) {
         DLE_CHECK_ARG(ht[i].numel == pl->stage_numel[i] && ht[i].grad && ht[i].param && ht[i].exp_avg && ht[i].exp_avg_sq);
         t[i] = LambTensorDev{ht[i].grad, ht[i].param, ht[i].exp_avg, ht[i].exp_avg_sq, ht[i].model_param, ht[i].numel, ht[i].group, 0};
     }
-    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (cudaMemcpyAsync(pl->tensors, t, sizeof(LambTensorDev) * n_tensors, cudaMemcpyHostToDevice, s) != cudaSuccess) return DLE_ERR_CUDA;
-    if (!pl->stage_event && cudaEventCreateWithFlags(&pl->stage_event, cudaEventDisableTiming) != cudaSuccess) return DLE_ERR_CUDA;
-    if (cudaEventRecord(pl->stage_event, s) != cudaSuccess) return DLE_ERR_CUDA;
+    if (cap != cudaStreamCaptureStatusActive) {
+        if (cudaEventRecord(pl->stage_event[slot], s) != cudaSuccess) return DLE_ERR_CUDA;
+        pl->stage_used[slot] = true;
+    }
     return DLE_OK;
 }
 
@@ -406,7 +429,7 @@ extern "C" int dle_lamb_plan_destroy(void* plan) {
     LambPlan* pl = static_cast<LambPlan*>(plan);
     cudaFree(pl->block);
     if (pl->host_stage) cudaFreeHost(pl->host_stage);
-    if (pl->stage_event) cudaEventDestroy(pl->stage_event);
+    for (int i = 0; i < LAMB_EAGER_SLOTS; ++i) if (pl->stage_event[i]) cudaEventDestroy(pl->stage_event[i]);
     delete[] pl->stage_numel;
     delete pl;
     return DLE_OK;

@@ -53,7 +53,8 @@ __global__ void __launch_bounds__(LN_THREADS)
 add_ln_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ bias, const bf16* __restrict__ residual,
                   const bf16* __restrict__ gamma, const bf16* __restrict__ beta, bf16* __restrict__ z_out,
                   bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, long long T, float eps,
-                  uint32_t thresh, float drop_scale, unsigned long long seed, uint32_t stream_id) {
+                  uint32_t thresh, float drop_scale, unsigned long long seed, const unsigned long long* seed_dev, uint32_t stream_id) {
+    seed = effective_seed(seed, seed_dev);
     constexpr int H = J * 256;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float gm[J * 8], bt[J * 8], bs[J * 8];
@@ -77,7 +78,7 @@ add_ln_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ bias, con
 #pragma unroll
             for (int i = 0; i < 8; ++i) z[j * 8 + i] += bs[j * 8 + i];
             if (thresh != 0u) {
-                const uint32_t keep = ((dropout_keep32(seed, stream_id, (unsigned long long)(row * H + col) >> 5, thresh) >> (col & 31)) & 0xffu);
+                const uint32_t keep = dropout_keep8(seed, stream_id, (unsigned long long)(row * H + col) >> 5, (col & 31) >> 3, thresh);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) z[j * 8 + i] = ((keep >> i) & 1u) ? z[j * 8 + i] * drop_scale : 0.f;
             }
@@ -116,7 +117,8 @@ add_ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, const
                   const float* __restrict__ rstd_in, const bf16* __restrict__ gamma, bf16* __restrict__ dz_out,
                   bf16* __restrict__ dx_out, float* __restrict__ part_dgamma, float* __restrict__ part_dbeta,
                   float* __restrict__ part_dbias, long long T, uint32_t thresh, float drop_scale,
-                  unsigned long long seed, uint32_t stream_id) {
+                  unsigned long long seed, const unsigned long long* seed_dev, uint32_t stream_id) {
+    seed = effective_seed(seed, seed_dev);
     constexpr int H = J * 256;
     __shared__ float red[LN_WARPS][H];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -156,7 +158,7 @@ add_ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, const
             for (int i = 0; i < 8; ++i) dzv[i] = rstd * (g[j * 8 + i] - s1 - xh[j * 8 + i] * s2);
             if (dz_out) *reinterpret_cast<uint4*>(dz_out + row * H + col) = pack8(dzv);
             if (thresh != 0u) {
-                const uint32_t keep = ((dropout_keep32(seed, stream_id, (unsigned long long)(row * H + col) >> 5, thresh) >> (col & 31)) & 0xffu);
+                const uint32_t keep = dropout_keep8(seed, stream_id, (unsigned long long)(row * H + col) >> 5, (col & 31) >> 3, thresh);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) dzv[i] = ((keep >> i) & 1u) ? dzv[i] * drop_scale : 0.f;
                 if (dx_out) *reinterpret_cast<uint4*>(dx_out + row * H + col) = pack8(dzv);
@@ -204,7 +206,8 @@ __global__ void __launch_bounds__(LN2_THREADS)
 add_ln_fwd2_kernel(const bf16* __restrict__ x, const bf16* __restrict__ bias, const bf16* __restrict__ residual,
                    const bf16* __restrict__ gamma, const bf16* __restrict__ beta, bf16* __restrict__ z_out,
                    bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, long long T, float eps,
-                   uint32_t thresh, float drop_scale, unsigned long long seed, uint32_t stream_id) {
+                   uint32_t thresh, float drop_scale, unsigned long long seed, const unsigned long long* seed_dev, uint32_t stream_id) {
+    seed = effective_seed(seed, seed_dev);
     constexpr int H = J2 * 512;
     __shared__ float ex[2][LN2_ROWS][2][2];        // [parity][row group][warp of the pair][slot]
     const int t64 = threadIdx.x & 63, rg = threadIdx.x >> 6, wp = (threadIdx.x >> 5) & 1, lane = threadIdx.x & 31;
@@ -229,7 +232,7 @@ add_ln_fwd2_kernel(const bf16* __restrict__ x, const bf16* __restrict__ bias, co
 #pragma unroll
             for (int i = 0; i < 8; ++i) z[j * 8 + i] += b[i];
             if (thresh != 0u) {
-                const uint32_t keep = (dropout_keep32(seed, stream_id, (unsigned long long)(row * H + col) >> 5, thresh) >> (col & 31)) & 0xffu;
+                const uint32_t keep = dropout_keep8(seed, stream_id, (unsigned long long)(row * H + col) >> 5, (col & 31) >> 3, thresh);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) z[j * 8 + i] = ((keep >> i) & 1u) ? z[j * 8 + i] * drop_scale : 0.f;
             }
@@ -276,7 +279,8 @@ add_ln_bwd2_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, cons
                    const float* __restrict__ rstd_in, const bf16* __restrict__ gamma, bf16* __restrict__ dz_out,
                    bf16* __restrict__ dx_out, float* __restrict__ part_dgamma, float* __restrict__ part_dbeta,
                    float* __restrict__ part_dbias, long long T, uint32_t thresh, float drop_scale,
-                   unsigned long long seed, uint32_t stream_id) {
+                   unsigned long long seed, const unsigned long long* seed_dev, uint32_t stream_id) {
+    seed = effective_seed(seed, seed_dev);
     constexpr int H = J2 * 512;
     __shared__ float ex[2][LN2_ROWS][2][2];
     __shared__ float red[LN2_ROWS][H];
@@ -324,7 +328,7 @@ add_ln_bwd2_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, cons
             for (int i = 0; i < 8; ++i) dzv[i] = rstd * (g[j * 8 + i] - s1 - xh[j * 8 + i] * s2);
             if (dz_out) *reinterpret_cast<uint4*>(dz_out + row * H + col) = pack8(dzv);
             if (thresh != 0u) {
-                const uint32_t keep = (dropout_keep32(seed, stream_id, (unsigned long long)(row * H + col) >> 5, thresh) >> (col & 31)) & 0xffu;
+                const uint32_t keep = dropout_keep8(seed, stream_id, (unsigned long long)(row * H + col) >> 5, (col & 31) >> 3, thresh);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) dzv[i] = ((keep >> i) & 1u) ? dzv[i] * drop_scale : 0.f;
                 if (dx_out) *reinterpret_cast<uint4*>(dx_out + row * H + col) = pack8(dzv);
@@ -464,7 +468,8 @@ embed_ln_fwd_kernel(const long long* __restrict__ ids, const long long* __restri
                     const bf16* __restrict__ pos, const bf16* __restrict__ type, const bf16* __restrict__ gamma,
                     const bf16* __restrict__ beta, bf16* __restrict__ z_out, bf16* __restrict__ y, float* __restrict__ mean_out,
                     float* __restrict__ rstd_out, int B, int S, int V, int P, int NT, float eps, uint32_t thresh,
-                    float drop_scale, unsigned long long seed, uint32_t stream_id, int* err_flag) {
+                    float drop_scale, unsigned long long seed, const unsigned long long* seed_dev, uint32_t stream_id, int* err_flag) {
+    seed = effective_seed(seed, seed_dev);
     constexpr int H = J * 256;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long T = (long long)B * S;
@@ -503,7 +508,7 @@ embed_ln_fwd_kernel(const long long* __restrict__ ids, const long long* __restri
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[i] = (z[j * 8 + i] - mean) * rstd * gm[j * 8 + i] + bt[j * 8 + i];
             if (thresh != 0u) {
-                const uint32_t keep = ((dropout_keep32(seed, stream_id, (unsigned long long)(row * H + col) >> 5, thresh) >> (col & 31)) & 0xffu);
+                const uint32_t keep = dropout_keep8(seed, stream_id, (unsigned long long)(row * H + col) >> 5, (col & 31) >> 3, thresh);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) o[i] = ((keep >> i) & 1u) ? o[i] * drop_scale : 0.f;
             }
@@ -518,7 +523,8 @@ embed_ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, con
                     const float* __restrict__ rstd_in, const bf16* __restrict__ gamma, const long long* __restrict__ ids,
                     const long long* __restrict__ tts, float* __restrict__ dword, float* __restrict__ dpos,
                     float* __restrict__ dtype_tab, float* __restrict__ part_dgamma, float* __restrict__ part_dbeta,
-                    int B, int S, uint32_t thresh, float drop_scale, unsigned long long seed, uint32_t stream_id) {
+                    int B, int S, uint32_t thresh, float drop_scale, unsigned long long seed, const unsigned long long* seed_dev, uint32_t stream_id) {
+    seed = effective_seed(seed, seed_dev);
     constexpr int H = J * 256;
     __shared__ float red[LN_WARPS][H];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -540,7 +546,7 @@ embed_ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, con
             unpack8(ld_global_nc_v4(dy + row * H + col), d);
             unpack8(ld_global_nc_v4(z + row * H + col), zz);
             if (thresh != 0u) {
-                const uint32_t keep = ((dropout_keep32(seed, stream_id, (unsigned long long)(row * H + col) >> 5, thresh) >> (col & 31)) & 0xffu);
+                const uint32_t keep = dropout_keep8(seed, stream_id, (unsigned long long)(row * H + col) >> 5, (col & 31) >> 3, thresh);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) d[i] = ((keep >> i) & 1u) ? d[i] * drop_scale : 0.f;
             }
@@ -600,6 +606,10 @@ __global__ void gather_rows_kernel(const bf16* __restrict__ x, const long long* 
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / vec_per_row; const int c = (int)(i - r * vec_per_row);
         long long src = idx[r];
+        if (src == -1) {                                          // padding slot (static-size index lists): zero row, not an error
+            *reinterpret_cast<uint4*>(out + r * H + c * 8) = make_uint4(0u, 0u, 0u, 0u);
+            continue;
+        }
         if (src < 0 || src >= n_rows) { if (err_flag) atomicExch(err_flag, 1); src = 0; }
         *reinterpret_cast<uint4*>(out + r * H + c * 8) = ld_global_nc_v4(x + src * H + c * 8);
     }
@@ -657,7 +667,7 @@ using namespace dle;
 
 extern "C" int dle_add_ln_fwd(const void* x, const void* bias, const void* residual, const void* gamma, const void* beta,
                               void* z_out, void* y, float* mean, float* rstd, int64_t T, int32_t H, float eps,
-                              float dropout_p, uint64_t seed, uint32_t dropout_stream, void* stream) {
+                              float dropout_p, uint64_t seed, const uint64_t* seed_dev, uint32_t dropout_stream, void* stream) {
     DLE_CHECK_ARG(x && gamma && beta && y && mean && rstd && T > 0 && H > 0 && H % 256 == 0 && H <= 1024);
     DLE_CHECK_ARG(ALIGNED16(x) && ALIGNED16(y) && ALIGNED16(gamma) && ALIGNED16(beta) && ALIGNED16(bias) && ALIGNED16(residual) && ALIGNED16(z_out));
     DLE_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f);
@@ -665,13 +675,13 @@ extern "C" int dle_add_ln_fwd(const void* x, const void* bias, const void* resid
     const uint32_t th = dropout_p > 0.f ? dropout_thresh16(dropout_p) : 0u;
     const float sc = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
     if (H % 512 == 0 && !ln_force_one_warp()) {
-        if (H == 1024) add_ln_fwd2_kernel<2><<<ln2_grid(T), LN2_THREADS, 0, S_(stream)>>>(B_(x), B_(bias), B_(residual), B_(gamma), B_(beta), BM_(z_out), BM_(y), mean, rstd, T, eps, th, sc, seed, dropout_stream);
-        else add_ln_fwd2_kernel<1><<<ln2_grid(T), LN2_THREADS, 0, S_(stream)>>>(B_(x), B_(bias), B_(residual), B_(gamma), B_(beta), BM_(z_out), BM_(y), mean, rstd, T, eps, th, sc, seed, dropout_stream);
+        if (H == 1024) add_ln_fwd2_kernel<2><<<ln2_grid(T), LN2_THREADS, 0, S_(stream)>>>(B_(x), B_(bias), B_(residual), B_(gamma), B_(beta), BM_(z_out), BM_(y), mean, rstd, T, eps, th, sc, seed, reinterpret_cast<const unsigned long long*>(seed_dev), dropout_stream);
+        else add_ln_fwd2_kernel<1><<<ln2_grid(T), LN2_THREADS, 0, S_(stream)>>>(B_(x), B_(bias), B_(residual), B_(gamma), B_(beta), BM_(z_out), BM_(y), mean, rstd, T, eps, th, sc, seed, reinterpret_cast<const unsigned long long*>(seed_dev), dropout_stream);
         DLE_LAUNCH_CHECK();
         return DLE_OK;
     }
     LN_DISPATCH(H, (add_ln_fwd_kernel<J><<<ln_grid(T), LN_THREADS, 0, S_(stream)>>>(B_(x), B_(bias), B_(residual), B_(gamma), B_(beta),
-                    BM_(z_out), BM_(y), mean, rstd, T, eps, th, sc, seed, dropout_stream)));
+                    BM_(z_out), BM_(y), mean, rstd, T, eps, th, sc, seed, reinterpret_cast<const unsigned long long*>(seed_dev), dropout_stream)));
     DLE_LAUNCH_CHECK();
     return DLE_OK;
 }
@@ -683,7 +693,7 @@ extern "C" int dle_ln_bwd_partials_h(int64_t T, int32_t H) { return (H % 512 == 
 
 extern "C" int dle_add_ln_bwd(const void* dy, const void* z, const float* mean, const float* rstd, const void* gamma,
                               void* dz_out, void* dx_out, float* part_dgamma, float* part_dbeta, float* part_dbias,
-                              int64_t T, int32_t H, float dropout_p, uint64_t seed, uint32_t dropout_stream, void* stream) {
+                              int64_t T, int32_t H, float dropout_p, uint64_t seed, const uint64_t* seed_dev, uint32_t dropout_stream, void* stream) {
     DLE_CHECK_ARG(dy && z && mean && rstd && gamma && T > 0 && H > 0 && H % 256 == 0 && H <= 1024);
     DLE_CHECK_ARG(ALIGNED16(dy) && ALIGNED16(z) && ALIGNED16(gamma) && ALIGNED16(dz_out) && ALIGNED16(dx_out));
     DLE_CHECK_ARG(dz_out != nullptr || dx_out != nullptr);
@@ -693,13 +703,13 @@ extern "C" int dle_add_ln_bwd(const void* dy, const void* z, const float* mean, 
     const uint32_t th = dropout_p > 0.f ? dropout_thresh16(dropout_p) : 0u;
     const float sc = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
     if (H % 512 == 0 && !ln_force_one_warp()) {
-        if (H == 1024) add_ln_bwd2_kernel<2><<<ln2_grid(T), LN2_THREADS, 0, S_(stream)>>>(B_(dy), B_(z), mean, rstd, B_(gamma), BM_(dz_out), BM_(dx_out), part_dgamma, part_dbeta, part_dbias, T, th, sc, seed, dropout_stream);
-        else add_ln_bwd2_kernel<1><<<ln2_grid(T), LN2_THREADS, 0, S_(stream)>>>(B_(dy), B_(z), mean, rstd, B_(gamma), BM_(dz_out), BM_(dx_out), part_dgamma, part_dbeta, part_dbias, T, th, sc, seed, dropout_stream);
+        if (H == 1024) add_ln_bwd2_kernel<2><<<ln2_grid(T), LN2_THREADS, 0, S_(stream)>>>(B_(dy), B_(z), mean, rstd, B_(gamma), BM_(dz_out), BM_(dx_out), part_dgamma, part_dbeta, part_dbias, T, th, sc, seed, reinterpret_cast<const unsigned long long*>(seed_dev), dropout_stream);
+        else add_ln_bwd2_kernel<1><<<ln2_grid(T), LN2_THREADS, 0, S_(stream)>>>(B_(dy), B_(z), mean, rstd, B_(gamma), BM_(dz_out), BM_(dx_out), part_dgamma, part_dbeta, part_dbias, T, th, sc, seed, reinterpret_cast<const unsigned long long*>(seed_dev), dropout_stream);
         DLE_LAUNCH_CHECK();
         return DLE_OK;
     }
     LN_DISPATCH(H, (add_ln_bwd_kernel<J><<<ln_grid(T), LN_THREADS, 0, S_(stream)>>>(B_(dy), B_(z), mean, rstd, B_(gamma), BM_(dz_out),
-                    BM_(dx_out), part_dgamma, part_dbeta, part_dbias, T, th, sc, seed, dropout_stream)));
+                    BM_(dx_out), part_dgamma, part_dbeta, part_dbias, T, th, sc, seed, reinterpret_cast<const unsigned long long*>(seed_dev), dropout_stream)));
     DLE_LAUNCH_CHECK();
     return DLE_OK;
 }
@@ -743,7 +753,7 @@ extern "C" int dle_bias_gelu_bwd(const void* dy, const void* u, void* du, int64_
 extern "C" int dle_embed_ln_fwd(const int64_t* input_ids, const int64_t* token_type_ids, const void* word, const void* pos,
                                 const void* type, const void* gamma, const void* beta, void* z_out, void* y, float* mean,
                                 float* rstd, int32_t B, int32_t S, int32_t H, int32_t V, int32_t P, int32_t NT, float eps,
-                                float dropout_p, uint64_t seed, uint32_t dropout_stream, int32_t* err_flag, void* stream) {
+                                float dropout_p, uint64_t seed, const uint64_t* seed_dev, uint32_t dropout_stream, int32_t* err_flag, void* stream) {
     DLE_CHECK_ARG(input_ids && token_type_ids && word && pos && type && gamma && beta && y && mean && rstd);
     DLE_CHECK_ARG(B > 0 && S > 0 && H % 256 == 0 && H > 0 && H <= 1024 && V > 0 && P >= S && NT > 0);
     DLE_CHECK_ARG(ALIGNED16(word) && ALIGNED16(pos) && ALIGNED16(type) && ALIGNED16(y) && ALIGNED16(z_out) && ALIGNED16(gamma) && ALIGNED16(beta));
@@ -753,7 +763,7 @@ extern "C" int dle_embed_ln_fwd(const int64_t* input_ids, const int64_t* token_t
     const long long T = (long long)B * S;
     LN_DISPATCH(H, (embed_ln_fwd_kernel<J><<<ln_grid(T), LN_THREADS, 0, S_(stream)>>>(
                     reinterpret_cast<const long long*>(input_ids), reinterpret_cast<const long long*>(token_type_ids), B_(word), B_(pos),
-                    B_(type), B_(gamma), B_(beta), BM_(z_out), BM_(y), mean, rstd, B, S, V, P, NT, eps, th, sc, seed, dropout_stream, err_flag)));
+                    B_(type), B_(gamma), B_(beta), BM_(z_out), BM_(y), mean, rstd, B, S, V, P, NT, eps, th, sc, seed, reinterpret_cast<const unsigned long long*>(seed_dev), dropout_stream, err_flag)));
     DLE_LAUNCH_CHECK();
     return DLE_OK;
 }
@@ -761,7 +771,7 @@ extern "C" int dle_embed_ln_fwd(const int64_t* input_ids, const int64_t* token_t
 extern "C" int dle_embed_ln_bwd(const void* dy, const void* z, const float* mean, const float* rstd, const void* gamma,
                                 const int64_t* input_ids, const int64_t* token_type_ids, float* dword, float* dpos,
                                 float* dtype_tab, float* part_dgamma, float* part_dbeta, int32_t B, int32_t S, int32_t H,
-                                float dropout_p, uint64_t seed, uint32_t dropout_stream, void* stream) {
+                                float dropout_p, uint64_t seed, const uint64_t* seed_dev, uint32_t dropout_stream, void* stream) {
     DLE_CHECK_ARG(dy && z && mean && rstd && gamma && input_ids && token_type_ids && dword && dpos && dtype_tab && part_dgamma && part_dbeta);
     DLE_CHECK_ARG(B > 0 && S > 0 && H % 256 == 0 && H > 0 && H <= 1024 && ALIGNED16(dy) && ALIGNED16(z) && ALIGNED16(dword) && ALIGNED16(dpos) && ALIGNED16(dtype_tab));
     const uint32_t th = dropout_p > 0.f ? dropout_thresh16(dropout_p) : 0u;
@@ -770,7 +780,7 @@ extern "C" int dle_embed_ln_bwd(const void* dy, const void* z, const float* mean
     LN_DISPATCH(H, (embed_ln_bwd_kernel<J><<<ln_grid(T), LN_THREADS, 0, S_(stream)>>>(
                     B_(dy), B_(z), mean, rstd, B_(gamma), reinterpret_cast<const long long*>(input_ids),
                     reinterpret_cast<const long long*>(token_type_ids), dword, dpos, dtype_tab, part_dgamma, part_dbeta, B, S, th, sc,
-                    seed, dropout_stream)));
+                    seed, reinterpret_cast<const unsigned long long*>(seed_dev), dropout_stream)));
     DLE_LAUNCH_CHECK();
     return DLE_OK;
 }
@@ -787,6 +797,13 @@ extern "C" int dle_scatter_rows(const void* dy, const int64_t* idx, void* dx, in
     DLE_CHECK_ARG(dy && idx && dx && n_idx >= 0 && H > 0 && H % 8 == 0 && n_rows > 0 && ALIGNED16(dy) && ALIGNED16(dx));
     if (n_idx == 0) return DLE_OK;
     scatter_rows_kernel<<<ew_grid(n_idx * (H / 8), 256), 256, 0, S_(stream)>>>(B_(dy), reinterpret_cast<const long long*>(idx), BM_(dx), n_idx, H, n_rows);
+    DLE_LAUNCH_CHECK();
+    return DLE_OK;
+}
+__global__ void advance_u64_kernel(unsigned long long* c, unsigned long long d) { *c += d; }
+extern "C" int dle_advance_u64(uint64_t* counter, uint64_t delta, void* stream) {
+    DLE_CHECK_ARG(counter && (reinterpret_cast<uintptr_t>(counter) & 7) == 0);
+    advance_u64_kernel<<<1, 1, 0, S_(stream)>>>(reinterpret_cast<unsigned long long*>(counter), delta);
     DLE_LAUNCH_CHECK();
     return DLE_OK;
 }

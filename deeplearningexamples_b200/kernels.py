@@ -41,7 +41,7 @@ def _row_major_2d(t, name):
 # GEMM
 # ------------------------------------------------------------------------------------------------
 def gemm(a, b, *, a_layout=L.LAYOUT_K, b_layout=L.LAYOUT_K, epilogue=L.EPI_BIAS, bias=None, aux=None,
-         out=None, out2=None, splits=1, tile_n=0, alpha=1.0, dropout_p=0.0, seed=0, dropout_stream=0, colsum_out=None):
+         out=None, out2=None, splits=1, tile_n=0, alpha=1.0, dropout_p=0.0, seed=0, seed_dev=None, dropout_stream=0, colsum_out=None):
     """D[M,N] = alpha * A x B^T with fused epilogue (see include/dle_b200.h).
 
     a: [M,K] (LAYOUT_K) or [K,M] (LAYOUT_MN);  b: [N,K] (LAYOUT_K) or [K,N] (LAYOUT_MN)."""
@@ -73,6 +73,7 @@ def gemm(a, b, *, a_layout=L.LAYOUT_K, b_layout=L.LAYOUT_K, epilogue=L.EPI_BIAS,
     args.epilogue, args.splits, args.tile_n = epilogue, splits, tile_n
     args.alpha, args.dropout_p = alpha, dropout_p
     args.dropout_stream, args.seed = dropout_stream, seed
+    args.seed_dev = 0 if seed_dev is None else seed_dev.data_ptr()
     args.colsum_out = 0 if colsum_out is None else _req(colsum_out, torch.float32, "colsum_out").data_ptr()
     if gemm_profile is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -87,7 +88,7 @@ def gemm(a, b, *, a_layout=L.LAYOUT_K, b_layout=L.LAYOUT_K, epilogue=L.EPI_BIAS,
 # ------------------------------------------------------------------------------------------------
 # attention
 # ------------------------------------------------------------------------------------------------
-def attn_fwd(qkv, mask, B, S, A, dropout_p=0.0, seed=0, dropout_stream=0, seq_first=False):
+def attn_fwd(qkv, mask, B, S, A, dropout_p=0.0, seed=0, dropout_stream=0, seq_first=False, seed_dev=None):
     lib = L.load()
     _req(qkv, bf16, "qkv")
     ctx = torch.empty((B * S, A * 64), device=qkv.device, dtype=bf16)
@@ -95,17 +96,18 @@ def attn_fwd(qkv, mask, B, S, A, dropout_p=0.0, seed=0, dropout_stream=0, seq_fi
     if mask is not None:
         _req(mask, torch.float32, "mask")
     L.launch_count["n"] += 1; L.check(lib.dle_attn_fwd(_ptr(qkv), _ptr(mask), _ptr(ctx), _ptr(lse), B, S, A, 1 if seq_first else 0, dropout_p, seed,
-                             dropout_stream, _stream()), "dle_attn_fwd")
+                             _ptr(seed_dev), dropout_stream, _stream()), "dle_attn_fwd")
     return ctx, lse
 
 
-def attn_bwd(qkv, mask, ctx, dctx, lse, B, S, A, dropout_p=0.0, seed=0, dropout_stream=0, seq_first=False, dbias=None):
+def attn_bwd(qkv, mask, ctx, dctx, lse, B, S, A, dropout_p=0.0, seed=0, dropout_stream=0, seq_first=False, dbias=None, seed_dev=None):
     """dbias: optional zeroed fp32 [3H] receiving the column sums of dqkv (q/k/v bias gradients)."""
     lib = L.load()
     dqkv = torch.empty_like(qkv)
-    delta = torch.empty((B, A, S), device=qkv.device, dtype=torch.float32)
+    # row dots [B,A,S] followed by the fp32 dQ accumulator [B,A,S,64] the kernel sums over the key tiles (include/dle_b200.h)
+    delta = torch.empty(B * A * S * (65 if S > 128 else 1), device=qkv.device, dtype=torch.float32)
     L.launch_count["n"] += 2; L.check(lib.dle_attn_bwd(_ptr(qkv), _ptr(mask), _ptr(ctx), _ptr(_req(dctx, bf16, "dctx")), _ptr(lse), _ptr(dqkv),
-                             _ptr(delta), _ptr(dbias), B, S, A, 1 if seq_first else 0, dropout_p, seed, dropout_stream, _stream()), "dle_attn_bwd")
+                             _ptr(delta), _ptr(dbias), B, S, A, 1 if seq_first else 0, dropout_p, seed, _ptr(seed_dev), dropout_stream, _stream()), "dle_attn_bwd")
     return dqkv
 
 
@@ -113,7 +115,7 @@ def attn_bwd(qkv, mask, ctx, dctx, lse, B, S, A, dropout_p=0.0, seed=0, dropout_
 # LayerNorm family
 # ------------------------------------------------------------------------------------------------
 def add_ln_fwd(x, gamma, beta, *, bias=None, residual=None, eps=1e-12, dropout_p=0.0, seed=0, dropout_stream=0,
-               save_z=True):
+               save_z=True, seed_dev=None):
     lib = L.load()
     _req(x, bf16, "x")
     T, H = x.shape
@@ -123,11 +125,11 @@ def add_ln_fwd(x, gamma, beta, *, bias=None, residual=None, eps=1e-12, dropout_p
     mean = torch.empty(T, device=x.device, dtype=torch.float32)
     rstd = torch.empty(T, device=x.device, dtype=torch.float32)
     L.launch_count["n"] += 1; L.check(lib.dle_add_ln_fwd(_ptr(x), _ptr(bias), _ptr(residual), _ptr(gamma), _ptr(beta), _ptr(z), _ptr(y), _ptr(mean),
-                               _ptr(rstd), T, H, eps, dropout_p, seed, dropout_stream, _stream()), "dle_add_ln_fwd")
+                               _ptr(rstd), T, H, eps, dropout_p, seed, _ptr(seed_dev), dropout_stream, _stream()), "dle_add_ln_fwd")
     return y, (z if z is not None else x), mean, rstd
 
 
-def add_ln_bwd(dy, z, mean, rstd, gamma, *, dropout_p=0.0, seed=0, dropout_stream=0, want_dbias=True, out_dtype=torch.float32):
+def add_ln_bwd(dy, z, mean, rstd, gamma, *, dropout_p=0.0, seed=0, dropout_stream=0, want_dbias=True, out_dtype=torch.float32, seed_dev=None):
     """returns dz, dx (== dz when no dropout), dgamma, dbeta, dbias ([H] each, fp32 or bf16 per out_dtype)."""
     lib = L.load()
     T, H = dy.shape
@@ -137,7 +139,7 @@ def add_ln_bwd(dy, z, mean, rstd, gamma, *, dropout_p=0.0, seed=0, dropout_strea
     dx = torch.empty_like(dy) if dropout_p > 0.0 else None
     L.launch_count["n"] += 1; L.check(lib.dle_add_ln_bwd(_ptr(dy), _ptr(z), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(dz), _ptr(dx), _ptr(parts[0]),
                                _ptr(parts[1]), _ptr(parts[2]) if want_dbias else None, T, H, dropout_p, seed,
-                               dropout_stream, _stream()), "dle_add_ln_bwd")
+                               _ptr(seed_dev), dropout_stream, _stream()), "dle_add_ln_bwd")
     na = 3 if want_dbias else 2
     red = torch.empty((na, H), device=dy.device, dtype=out_dtype)
     L.launch_count["n"] += 1; L.check(lib.dle_colsum_finalize_batched(_ptr(parts), na, n_part, H, _ptr(red), L.DLE_DTYPE_F32 if out_dtype == torch.float32 else L.DLE_DTYPE_BF16, 0, _stream()),
@@ -180,7 +182,7 @@ def bias_gelu_bwd(dy, u):
 # embeddings / gathers / casts
 # ------------------------------------------------------------------------------------------------
 def embed_ln_fwd(input_ids, token_type_ids, word, pos, typ, gamma, beta, *, eps=1e-12, dropout_p=0.0, seed=0,
-                 dropout_stream=0, err_flag=None):
+                 dropout_stream=0, err_flag=None, seed_dev=None):
     lib = L.load()
     _req(input_ids, torch.int64, "input_ids"); _req(token_type_ids, torch.int64, "token_type_ids"); _req(word, bf16, "word")
     B, S = input_ids.shape
@@ -192,11 +194,11 @@ def embed_ln_fwd(input_ids, token_type_ids, word, pos, typ, gamma, beta, *, eps=
     rstd = torch.empty(T, device=word.device, dtype=torch.float32)
     L.launch_count["n"] += 1; L.check(lib.dle_embed_ln_fwd(_ptr(input_ids), _ptr(token_type_ids), _ptr(word), _ptr(pos), _ptr(typ), _ptr(gamma), _ptr(beta),
                                  _ptr(z), _ptr(y), _ptr(mean), _ptr(rstd), B, S, H, word.shape[0], pos.shape[0], typ.shape[0],
-                                 eps, dropout_p, seed, dropout_stream, _ptr(err_flag), _stream()), "dle_embed_ln_fwd")
+                                 eps, dropout_p, seed, _ptr(seed_dev), dropout_stream, _ptr(err_flag), _stream()), "dle_embed_ln_fwd")
     return y, z, mean, rstd
 
 
-def embed_ln_bwd(dy, z, mean, rstd, gamma, input_ids, token_type_ids, V, P, NT, *, dropout_p=0.0, seed=0, dropout_stream=0):
+def embed_ln_bwd(dy, z, mean, rstd, gamma, input_ids, token_type_ids, V, P, NT, *, dropout_p=0.0, seed=0, dropout_stream=0, seed_dev=None):
     """returns fp32 dword [V,H], dpos [P,H], dtype [NT,H], dgamma [H], dbeta [H]."""
     lib = L.load()
     B, S = input_ids.shape
@@ -208,7 +210,7 @@ def embed_ln_bwd(dy, z, mean, rstd, gamma, input_ids, token_type_ids, V, P, NT, 
     parts = torch.empty((2, n_part, H), device=dy.device, dtype=torch.float32)
     L.launch_count["n"] += 1; L.check(lib.dle_embed_ln_bwd(_ptr(dy), _ptr(z), _ptr(mean), _ptr(rstd), _ptr(gamma), _ptr(input_ids), _ptr(token_type_ids),
                                  _ptr(dword), _ptr(dpos), _ptr(dtyp), _ptr(parts[0]), _ptr(parts[1]), B, S, H, dropout_p, seed,
-                                 dropout_stream, _stream()), "dle_embed_ln_bwd")
+                                 _ptr(seed_dev), dropout_stream, _stream()), "dle_embed_ln_bwd")
     red = torch.empty((2, H), device=dy.device, dtype=torch.float32)
     L.launch_count["n"] += 1; L.check(lib.dle_colsum_finalize_batched(_ptr(parts), 2, n_part, H, _ptr(red), L.DLE_DTYPE_F32, 0, _stream()),
                                       "dle_colsum_finalize_batched")
@@ -233,6 +235,13 @@ def scatter_rows(dy, idx, n_rows):
         return dx
     L.launch_count["n"] += 1; L.check(lib.dle_scatter_rows(_ptr(dy), _ptr(idx), _ptr(dx), idx.numel(), dy.shape[1], n_rows, _stream()), "dle_scatter_rows")
     return dx
+
+
+def advance_u64(counter, delta=1):
+    """counter (int64/uint64 device tensor, 1 element) += delta on the current stream; graph-capturable."""
+    lib = L.load()
+    _req(counter, None, "counter")
+    L.launch_count["n"] += 1; L.check(lib.dle_advance_u64(_ptr(counter), int(delta), _stream()), "dle_advance_u64")
 
 
 def cast_f32_to_bf16(x, out=None):

@@ -166,6 +166,17 @@ class FusedLAMBAMP(torch.optim.Optimizer):
                 if len(state) == 0:       # lazily created fp32 moments (fused_lamb.py:215-222)
                     state['exp_avg'] = torch.zeros_like(p.data, dtype=torch.float32)
                     state['exp_avg_sq'] = torch.zeros_like(p.data, dtype=torch.float32)
+                for key in ('exp_avg', 'exp_avg_sq'):
+                    # load_state_dict keeps whatever dtype a checkpoint held; the kernels take raw fp32 pointers
+                    st = state[key]
+                    if st.dtype != torch.float32 or st.device != p.device or not st.is_contiguous():
+                        state[key] = st.to(device=p.device, dtype=torch.float32).contiguous()
+                    if state[key].numel() != p.numel():
+                        raise RuntimeError('FusedLAMBAMP: optimizer state %s has %d elements for a parameter of %d'
+                                           % (key, state[key].numel(), p.numel()))
+                if p32 is not None and (p32.dtype != torch.float32 or p32.device != p.device or not p32.is_contiguous()
+                                        or p32.numel() != p.numel()):
+                    raise RuntimeError('FusedLAMBAMP: fp32 master copy does not match its parameter; call setup_fp32_params()')
                 master = p32 if p.dtype == torch.bfloat16 else p.data
                 if p.dtype == torch.bfloat16 and p32 is None:
                     raise RuntimeError('call setup_fp32_params() after casting the model to bf16')
@@ -225,9 +236,12 @@ class FusedLAMBAMP(torch.optim.Optimizer):
         if closure is not None:
             loss = closure()
         self._ensure_plan()
-        if self._plan is None:
-            return loss
         device = self.param_groups[0]["params"][0].device
+        if self._plan is None:            # no parameter has a gradient: nothing to do, but GradScaler.update() still expects an inf record
+            if grad_scaler is not None and grad_scaler.is_enabled():
+                self._found_inf.zero_()
+                grad_scaler._per_optimizer_states[id(self)]["found_inf_per_device"] = {device: self._found_inf}
+            return loss
         for gi, group in enumerate(self.param_groups):
             lr = group['lr']
             if isinstance(lr, torch.Tensor):

@@ -496,15 +496,21 @@ class BertPreTrainingHeads(nn.Module):
         self.sequence_output_is_dense = sequence_output_is_dense
         # Optional static bound on the number of masked positions per batch (batch * max_predictions_per_seq).  When set, the row
         # indices come from torch.nonzero_static: no device->host sync (the reference's torch.nonzero drains the launch queue once
-        # per step).  Surplus slots point at token 0 ([CLS], never masked => label -1 => ignored by the criterion).
+        # per step) and static shapes for CUDA-graph capture.  Surplus slots hold index -1 = padding: the gather kernel writes a zero
+        # row, the scatter in backward skips them and the criterion gives them label -1 (ignored).  A batch with MORE masked positions
+        # than the bound would silently lose the excess: that is recorded in `mlm_overflow` (device flag, sticky) and raised by
+        # check_mlm_overflow(), which callers invoke at points that already synchronise (logging, checkpoint, end of run).
         self.static_masked_count = None
+        self.register_buffer("mlm_overflow", torch.zeros((), dtype=torch.int32), persistent=False)
 
     def forward(self, sequence_output, pooled_output, masked_lm_labels):
         if self.sequence_output_is_dense:
             # only the masked positions reach the vocabulary GEMM (reference modeling.py:588-591); bit-exact row gather
             flat = sequence_output.reshape(-1, sequence_output.shape[-1])
             if self.static_masked_count:
-                idx = torch.nonzero_static(masked_lm_labels.view(-1) != -1, size=int(self.static_masked_count), fill_value=0).squeeze(-1)
+                is_masked = masked_lm_labels.view(-1) != -1
+                idx = torch.nonzero_static(is_masked, size=int(self.static_masked_count), fill_value=-1).squeeze(-1)
+                self.mlm_overflow.logical_or_(is_masked.sum() > int(self.static_masked_count))
             else:
                 idx = torch.nonzero(masked_lm_labels.view(-1) != -1).squeeze(-1)
             prediction_scores = self.predictions(ops.GatherRowsFn.apply(flat, idx))
@@ -513,6 +519,13 @@ class BertPreTrainingHeads(nn.Module):
         # the 2-way NSP classifier is a [B,H]x[H,2] product: plain library call
         seq_relationship_score = self.seq_relationship(pooled_output.to(self.seq_relationship.weight.dtype))
         return prediction_scores, seq_relationship_score
+
+
+    def check_mlm_overflow(self):
+        """Host sync.  Raises if any batch so far held more masked positions than `static_masked_count`."""
+        if self.static_masked_count and int(self.mlm_overflow.item()) != 0:
+            raise L.DleError("a batch held more masked LM positions than static_masked_count=%d: the excess was dropped from the "
+                             "loss; raise --max_predictions_per_seq or unset static_masked_count" % int(self.static_masked_count))
 
 
 class BertPreTrainedModel(nn.Module):
@@ -524,6 +537,12 @@ class BertPreTrainedModel(nn.Module):
             raise ValueError("Parameter config in `{}(config)` should be an instance of class `BertConfig`.".format(
                 self.__class__.__name__))
         self.config = config
+
+    def half(self):
+        """16-bit parameters on this path are bf16: the reference driver's `model.half()` (run_pretraining.py:416-417, taken for
+        --allreduce_post_accumulation_fp16) therefore selects bfloat16 here, so the unmodified script drives the bf16 kernels.
+        fp16 parameters are not supported by the kernels (precision policy)."""
+        return self.bfloat16()
 
     def init_bert_weights(self, module):
         if isinstance(module, (nn.Linear, nn.Embedding)):
@@ -572,6 +591,8 @@ class BertModel(BertPreTrainedModel):
             attention_mask = torch.ones_like(input_ids)
         if token_type_ids is None:
             token_type_ids = torch.zeros_like(input_ids)
+        if self.training:
+            ops.advance_step(input_ids.device)      # fresh dropout masks per forward pass, also when this call is a CUDA-graph replay
         # additive mask [B,1,1,S]: 0 where attended, -10000 where masked (reference modeling.py:864-872)
         extended_attention_mask = attention_mask.unsqueeze(1).unsqueeze(2).to(torch.float32)
         extended_attention_mask = (1.0 - extended_attention_mask) * -10000.0

@@ -17,17 +17,63 @@ bf16 = torch.bfloat16
 # -------------------------------------------------------------------------------------------------
 # RNG bookkeeping for dropout: one 64-bit seed per forward call site, drawn from a host counter.
 # -------------------------------------------------------------------------------------------------
+# Under CUDA graphs the host seeds are frozen into the captured launches, so every dropout kernel additionally mixes in a DEVICE
+# step counter (one int64 per device, `step_counter`) that BertModel.forward bumps once per training forward pass
+# (dle_advance_u64, itself captured): replays draw fresh masks, and the backward of a step sees the value its forward saw.
+# -------------------------------------------------------------------------------------------------
 _rng = {"base": None, "counter": 0}
 _stream_ids = {"next": 1}
 _MASK64 = (1 << 64) - 1
+_step_counters = {}          # device index -> int64[1] tensor
+_err_flags = {}              # device index -> int32[1] tensor (out-of-range ids seen by the gather kernels)
 
 
 def manual_seed(seed):
-    """Reset the dropout RNG: base seed, per-call counter and the call-site stream-id allocator (so that a model built
-    and run after manual_seed(s) reproduces its masks exactly)."""
+    """Reset the dropout RNG: base seed, per-call counter, the device step counters and the call-site stream-id allocator
+    (so that a model built and run after manual_seed(s) reproduces its masks exactly)."""
     _rng["base"] = int(seed) & _MASK64
     _rng["counter"] = 0
     _stream_ids["next"] = 1
+    for t in _step_counters.values():
+        t.zero_()
+
+
+def step_counter(device):
+    """The device-resident dropout step counter of `device` (created on first use)."""
+    idx = torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    t = _step_counters.get(idx)
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int64, device=torch.device("cuda", idx))
+        _step_counters[idx] = t
+    return t
+
+
+def advance_step(device):
+    """Bump the device step counter (once per training forward pass; graph-capturable)."""
+    K.advance_u64(step_counter(device), 1)
+
+
+def err_flag(device):
+    """Persistent device flag set by the embedding / row-gather kernels when they meet an out-of-range id (the kernels clamp and
+    continue; the reference's nn.Embedding would device-assert).  Read it with check_device_errors() at points that already sync."""
+    idx = torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    t = _err_flags.get(idx)
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", idx))
+        _err_flags[idx] = t
+    return t
+
+
+def check_device_errors():
+    """Host sync: raise if any kernel reported an out-of-range token / type / row index since the last check."""
+    for idx, t in _err_flags.items():
+        if int(t.item()) != 0:
+            t.zero_()
+            raise L.DleError(f"cuda:{idx}: an embedding or row-gather kernel saw an out-of-range index (ids were clamped to row 0)")
 
 
 def next_seed():
@@ -143,7 +189,7 @@ class DenseDropoutAddLNFn(torch.autograd.Function):
     def forward(ctx, x, residual, weight, bias, gamma, beta, p_drop, eps, stream_id):
         seed = next_seed() if p_drop > 0.0 else 0
         z = K.gemm(x, w16(weight), bias=w16(bias), aux=residual, epilogue=L.EPI_BIAS_DROPOUT_RESIDUAL,
-                   dropout_p=p_drop, seed=seed, dropout_stream=stream_id)
+                   dropout_p=p_drop, seed=seed, dropout_stream=stream_id, seed_dev=step_counter(x.device))
         y, _, mean, rstd = K.add_ln_fwd(z, w16(gamma), w16(beta), eps=eps)
         ctx.save_for_backward(x, weight, bias, gamma, beta, z, mean, rstd)
         ctx.p_drop, ctx.seed, ctx.stream_id = p_drop, seed, stream_id
@@ -153,7 +199,7 @@ class DenseDropoutAddLNFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, weight, bias, gamma, beta, z, mean, rstd = ctx.saved_tensors
         dz, dh, dgamma, dbeta, dbias = K.add_ln_bwd(dy.contiguous(), z, mean, rstd, w16(gamma), dropout_p=ctx.p_drop,
-                                                    seed=ctx.seed, dropout_stream=ctx.stream_id)
+                                                    seed=ctx.seed, dropout_stream=ctx.stream_id, seed_dev=step_counter(z.device))
         dx = K.gemm(dh, w16(weight), b_layout=L.LAYOUT_MN)
         dw = wgrad(dh, x, weight.dtype)
         return (dx, dz, dw, _to_param_dtype(dbias, bias), _to_param_dtype(dgamma, gamma), _to_param_dtype(dbeta, beta),
@@ -172,7 +218,8 @@ class SelfAttentionFn(torch.autograd.Function):
         seed = next_seed() if p_drop > 0.0 else 0
         w, b = w16(w_packed, key=wq), w16(b_packed, key=bq)
         qkv = K.gemm(x, w, bias=b)
-        out, lse = K.attn_fwd(qkv, mask, B, S, A, dropout_p=p_drop, seed=seed, dropout_stream=stream_id, seq_first=seq_first)
+        out, lse = K.attn_fwd(qkv, mask, B, S, A, dropout_p=p_drop, seed=seed, dropout_stream=stream_id, seq_first=seq_first,
+                              seed_dev=step_counter(x.device))
         ctx.save_for_backward(x, w_packed, mask, qkv, out, lse)
         ctx.cfg = (B, S, A, p_drop, seed, stream_id, seq_first)
         ctx.params = (wq, bq)
@@ -184,7 +231,7 @@ class SelfAttentionFn(torch.autograd.Function):
         B, S, A, p_drop, seed, stream_id, seq_first = ctx.cfg
         wq, bq = ctx.params
         dqkv = K.attn_bwd(qkv, mask, out, dout.contiguous(), lse, B, S, A, dropout_p=p_drop, seed=seed,
-                          dropout_stream=stream_id, seq_first=seq_first)
+                          dropout_stream=stream_id, seq_first=seq_first, seed_dev=step_counter(x.device))
         dx = K.gemm(dqkv, w16(w_packed, key=wq), b_layout=L.LAYOUT_MN)
         dw = wgrad(dqkv, x, wq.dtype)                       # [3H, H]
         db = _to_param_dtype(K.colsum(dqkv), bq)            # [3H]
@@ -207,14 +254,15 @@ class BertLayerFn(torch.autograd.Function):
         seed_a = next_seed() if p_attn > 0.0 else 0
         seed_1 = next_seed() if p_hid > 0.0 else 0
         seed_2 = next_seed() if p_hid > 0.0 else 0
+        sdev = step_counter(x.device)
         qkv = K.gemm(x, w16(w_qkv, key=wq), bias=w16(b_qkv, key=bq))
-        att, lse = K.attn_fwd(qkv, mask, B, S, A, dropout_p=p_attn, seed=seed_a, dropout_stream=sid_attn, seq_first=seq_first)
+        att, lse = K.attn_fwd(qkv, mask, B, S, A, dropout_p=p_attn, seed=seed_a, dropout_stream=sid_attn, seq_first=seq_first, seed_dev=sdev)
         z1 = K.gemm(att, w16(wo), bias=w16(bo), aux=x, epilogue=L.EPI_BIAS_DROPOUT_RESIDUAL, dropout_p=p_hid, seed=seed_1,
-                    dropout_stream=sid_h1)
+                    dropout_stream=sid_h1, seed_dev=sdev)
         y1, _, mean1, rstd1 = K.add_ln_fwd(z1, w16(g1), w16(be1), eps=eps)
         g, u = K.gemm(y1, w16(w1), bias=w16(b1), epilogue=L.EPI_BIAS_GELU)
         z2 = K.gemm(g, w16(w2), bias=w16(b2), aux=y1, epilogue=L.EPI_BIAS_DROPOUT_RESIDUAL, dropout_p=p_hid, seed=seed_2,
-                    dropout_stream=sid_h2)
+                    dropout_stream=sid_h2, seed_dev=sdev)
         y2, _, mean2, rstd2 = K.add_ln_fwd(z2, w16(g2), w16(be2), eps=eps)
         ctx.save_for_backward(x, mask, qkv, att, lse, z1, mean1, rstd1, y1, u, g, z2, mean2, rstd2, w_qkv)
         ctx.params = (wq, bq, wo, bo, g1, be1, w1, b1, w2, b2, g2, be2)
@@ -229,13 +277,14 @@ class BertLayerFn(torch.autograd.Function):
         B, S, A, p_attn, p_hid, eps, sid_attn, sid_h1, sid_h2, seq_first = ctx.cfg
         seed_a, seed_1, seed_2 = ctx.seeds
         H_ = x.shape[1]
+        sdev = step_counter(x.device)
         # bias gradients of FFN1 (4H) and q|k|v (3H) are column sums of tensors produced below: the producing kernels accumulate
         # them (warp transpose-reduce + red.add) instead of a separate pass re-reading du / dqkv from HBM
         bias_acc = torch.zeros(w1.shape[0] + 3 * H_, device=x.device, dtype=torch.float32)
         db1_acc, dbqkv_acc = bias_acc[:w1.shape[0]], bias_acc[w1.shape[0]:]
         # ---- BertOutput
         dz2, dh2, dg2, dbe2, db2 = K.add_ln_bwd(dy2.contiguous(), z2, mean2, rstd2, w16(g2), dropout_p=p_hid, seed=seed_2,
-                                                dropout_stream=sid_h2, out_dtype=g2.dtype)
+                                                dropout_stream=sid_h2, out_dtype=g2.dtype, seed_dev=sdev)
         du = K.gemm(dh2, w16(w2), b_layout=L.LAYOUT_MN, epilogue=L.EPI_DGELU, aux=u, colsum_out=db1_acc)   # dgrad * gelu'(u)
         dw2 = wgrad(dh2, g, w2.dtype)
         # ---- BertIntermediate (+ residual branch of BertOutput folded into the epilogue)
@@ -243,12 +292,12 @@ class BertLayerFn(torch.autograd.Function):
         dw1 = wgrad(du, y1, w1.dtype)
         # ---- BertSelfOutput
         dz1, dh1, dg1, dbe1, dbo = K.add_ln_bwd(dy1, z1, mean1, rstd1, w16(g1), dropout_p=p_hid, seed=seed_1, dropout_stream=sid_h1,
-                                                out_dtype=g1.dtype)
+                                                out_dtype=g1.dtype, seed_dev=sdev)
         datt = K.gemm(dh1, w16(wo), b_layout=L.LAYOUT_MN)
         dwo = wgrad(dh1, att, wo.dtype)
         # ---- BertSelfAttention (+ residual branch of BertSelfOutput folded into the QKV dgrad epilogue)
         dqkv = K.attn_bwd(qkv, mask, att, datt, lse, B, S, A, dropout_p=p_attn, seed=seed_a, dropout_stream=sid_attn, seq_first=seq_first,
-                          dbias=dbqkv_acc)
+                          dbias=dbqkv_acc, seed_dev=sdev)
         dx = K.gemm(dqkv, w16(w_qkv, key=wq), b_layout=L.LAYOUT_MN, epilogue=L.EPI_ADD, aux=dz1)
         dwqkv = wgrad(dqkv, x, wq.dtype)
         bias_g = bias_acc if b1.dtype == torch.float32 else bias_acc.to(b1.dtype)
@@ -268,12 +317,11 @@ class EmbeddingLNFn(torch.autograd.Function):
     def forward(ctx, input_ids, token_type_ids, word, pos, typ, gamma, beta, p_drop, eps, stream_id):
         seed = next_seed() if p_drop > 0.0 else 0
         ids, tts = input_ids.contiguous(), token_type_ids.contiguous()
-        err = torch.zeros(1, dtype=torch.int32, device=word.device)
         y, z, mean, rstd = K.embed_ln_fwd(ids, tts, w16(word), w16(pos), w16(typ), w16(gamma), w16(beta), eps=eps,
-                                          dropout_p=p_drop, seed=seed, dropout_stream=stream_id, err_flag=err)
+                                          dropout_p=p_drop, seed=seed, dropout_stream=stream_id, err_flag=err_flag(word.device),
+                                          seed_dev=step_counter(word.device))
         ctx.save_for_backward(ids, tts, word, pos, typ, gamma, beta, z, mean, rstd)
         ctx.cfg = (p_drop, seed, stream_id)
-        ctx.err_flag = err              # checked lazily (no host sync in the hot loop)
         return y
 
     @staticmethod
@@ -282,7 +330,7 @@ class EmbeddingLNFn(torch.autograd.Function):
         p_drop, seed, stream_id = ctx.cfg
         dword, dpos, dtyp, dgamma, dbeta = K.embed_ln_bwd(dy.contiguous(), z, mean, rstd, w16(gamma), ids, tts,
                                                           word.shape[0], pos.shape[0], typ.shape[0], dropout_p=p_drop,
-                                                          seed=seed, dropout_stream=stream_id)
+                                                          seed=seed, dropout_stream=stream_id, seed_dev=step_counter(dy.device))
         cast = lambda g, p: g if p.dtype == torch.float32 else K.cast_f32_to_bf16(g)
         return (None, None, cast(dword, word), cast(dpos, pos), cast(dtyp, typ), _to_param_dtype(dgamma, gamma),
                 _to_param_dtype(dbeta, beta), None, None, None)
@@ -310,7 +358,7 @@ class GatherRowsFn(torch.autograd.Function):
     def forward(ctx, x, idx):
         ctx.save_for_backward(idx)
         ctx.n_rows = x.shape[0]
-        return K.gather_rows(x, idx)
+        return K.gather_rows(x, idx, err_flag=err_flag(x.device))
 
     @staticmethod
     def backward(ctx, dy):

@@ -40,18 +40,20 @@ class BertPretrainingCriterion(torch.nn.Module):
         self.sequence_output_is_dense = sequence_output_is_dense
 
     def forward(self, prediction_scores, seq_relationship_score, masked_lm_labels, next_sentence_labels):
+        # cross-entropy runs in fp32 on the bf16 logits, as it does under the reference's autocast (CE is on autocast's fp32 list;
+        # run_pretraining.py:519-522)
+        scores = prediction_scores.view(-1, self.vocab_size).float()
         if self.sequence_output_is_dense:
             # reference: labels[labels != -1] (boolean indexing => host sync).  Same rows, same order, without the sync: the
             # first `n` non-ignored positions, n = rows of the (already dense) prediction scores; surplus slots (static-count
-            # mode) read position 0, whose label is -1 and is ignored by the loss.
+            # mode, index -1) get label -1 and are ignored by the loss.
             flat = masked_lm_labels.view(-1)
-            n = prediction_scores.view(-1, self.vocab_size).shape[0]
-            idx = torch.nonzero_static(flat != -1, size=n, fill_value=0).squeeze(-1)
-            mlm_labels = flat[idx]
-            masked_lm_loss = self.loss_fn(prediction_scores.view(-1, self.vocab_size), mlm_labels.view(-1))
+            idx = torch.nonzero_static(flat != -1, size=scores.shape[0], fill_value=-1).squeeze(-1)
+            mlm_labels = torch.where(idx >= 0, flat[idx.clamp_min(0)], torch.full_like(idx, -1))
+            masked_lm_loss = self.loss_fn(scores, mlm_labels)
         else:
-            masked_lm_loss = self.loss_fn(prediction_scores.view(-1, self.vocab_size), masked_lm_labels.view(-1))
-        next_sentence_loss = self.loss_fn(seq_relationship_score.view(-1, 2), next_sentence_labels.view(-1))
+            masked_lm_loss = self.loss_fn(scores, masked_lm_labels.view(-1))
+        next_sentence_loss = self.loss_fn(seq_relationship_score.view(-1, 2).float(), next_sentence_labels.view(-1))
         return masked_lm_loss + next_sentence_loss
 
 

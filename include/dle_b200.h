@@ -10,6 +10,11 @@
  *  - numeric overflow in gradients is NOT an error: it is reported through the device-side
  *    found_inf flag exactly like the reference's noop_flag protocol.
  *  - activations are bf16 row-major [tokens, features], tokens ordered b*S + s.
+ *  - dropout: masks are regenerated, never stored.  Every dropout kernel takes a host `seed`, an RNG `dropout_stream` id (one per
+ *    call site) and an optional DEVICE counter `seed_dev` (NULL = unused): the effective seed is seed + *seed_dev * 0x9E3779B97F4A7C15.
+ *    The counter lets a captured CUDA graph (whose host arguments are frozen) draw fresh masks on every replay: bump it once per
+ *    training step with dle_advance_u64 (the reference gets the same effect from the Philox offset of torch's graph-safe generator,
+ *    run_pretraining.py:622-626).  Forward and backward of one step must see the same counter value.
  *
  * There is no C FFI in the reference for this path; each entry point cites the
  * reference Python/C++ site it replaces (paths relative to PyTorch/LanguageModeling/BERT/).
@@ -76,6 +81,7 @@ typedef struct dle_gemm_args {
     float dropout_p;       /* DLE_EPI_BIAS_DROPOUT_RESIDUAL: drop probability, 0 = off */
     uint32_t dropout_stream; /* RNG stream id (distinct per call site so masks differ per layer) */
     uint64_t seed;
+    const uint64_t* seed_dev; /* optional device step counter mixed into the seed (see Conventions), or NULL */
     void* colsum_out;      /* fp32 [N] or NULL: += column sums of the bf16 output (bias gradient of the producing layer), atomics */
 } dle_gemm_args;
 
@@ -94,12 +100,13 @@ int dle_gemm_bf16(const dle_gemm_args* host_args, void* stream);
  *   modeling.py:330-338,498) -- both are read in place through 3-D TMA maps.
  * ------------------------------------------------------------------------------------------ */
 int dle_attn_fwd(const void* qkv, const float* mask, void* ctx, float* lse, int32_t B, int32_t S, int32_t A,
-                 int32_t seq_first, float dropout_p, uint64_t seed, uint32_t dropout_stream, void* stream);
-/* delta_ws: fp32 workspace [B, A, S]; dqkv: bf16 [B*S, 3*A*64], fully overwritten;
+                 int32_t seq_first, float dropout_p, uint64_t seed, const uint64_t* seed_dev, uint32_t dropout_stream, void* stream);
+/* delta_ws: fp32 workspace of B*A*S*65 floats ([B,A,S] row dots followed by the [B,A,S,64] dQ accumulator; B*A*S suffices when S == 128);
+ * dqkv: bf16 [B*S, 3*A*64], fully overwritten;
  * dbias_qkv: fp32 [3*A*64] or NULL: += column sums of dqkv (the q/k/v bias gradients), must be zeroed by the caller */
 int dle_attn_bwd(const void* qkv, const float* mask, const void* ctx, const void* dctx, const float* lse,
                  void* dqkv, float* delta_ws, float* dbias_qkv, int32_t B, int32_t S, int32_t A, int32_t seq_first, float dropout_p,
-                 uint64_t seed, uint32_t dropout_stream, void* stream);
+                 uint64_t seed, const uint64_t* seed_dev, uint32_t dropout_stream, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (bias +) dropout + residual-add + LayerNorm, vectorised warp-shuffle kernels (HBM-bound)
@@ -112,7 +119,7 @@ int dle_attn_bwd(const void* qkv, const float* mask, const void* ctx, const void
  * ------------------------------------------------------------------------------------------ */
 int dle_add_ln_fwd(const void* x, const void* bias, const void* residual, const void* gamma, const void* beta,
                    void* z_out, void* y, float* mean, float* rstd, int64_t T, int32_t H, float eps,
-                   float dropout_p, uint64_t seed, uint32_t dropout_stream, void* stream);
+                   float dropout_p, uint64_t seed, const uint64_t* seed_dev, uint32_t dropout_stream, void* stream);
 /* backward: dz = dLN(dy); dx = dropout_bwd(dz) written to dx_out when dropout_p > 0 (else dx == dz
  * and dx_out may be NULL).  dz is also the gradient of the residual branch.  Column reductions are written as fp32 partials [n_part, H] into the caller's workspace:
  *   part_dgamma, part_dbeta, part_dbias (sum_t dx).  n_part = dle_ln_bwd_partials(T).  A second
@@ -121,7 +128,7 @@ int dle_ln_bwd_partials(int64_t T);             /* upper bound over H (workspace
 int dle_ln_bwd_partials_h(int64_t T, int32_t H); /* rows of partials actually written for this H */
 int dle_add_ln_bwd(const void* dy, const void* z, const float* mean, const float* rstd, const void* gamma,
                    void* dz_out, void* dx_out, float* part_dgamma, float* part_dbeta, float* part_dbias,
-                   int64_t T, int32_t H, float dropout_p, uint64_t seed, uint32_t dropout_stream, void* stream);
+                   int64_t T, int32_t H, float dropout_p, uint64_t seed, const uint64_t* seed_dev, uint32_t dropout_stream, void* stream);
 /* out[n] = sum_p part[p, n]; out dtype DLE_DTYPE_BF16 or DLE_DTYPE_F32; accumulate != 0 adds to out */
 int dle_colsum_finalize(const float* part, int32_t n_part, int32_t N, void* out, int32_t out_dtype,
                         int32_t accumulate, void* stream);
@@ -153,17 +160,21 @@ int dle_bias_gelu_bwd(const void* dy, const void* u, void* du, int64_t T, int32_
 int dle_embed_ln_fwd(const int64_t* input_ids, const int64_t* token_type_ids, const void* word, const void* pos,
                      const void* type, const void* gamma, const void* beta, void* z_out, void* y, float* mean,
                      float* rstd, int32_t B, int32_t S, int32_t H, int32_t V, int32_t P, int32_t NT, float eps,
-                     float dropout_p, uint64_t seed, uint32_t dropout_stream, int32_t* err_flag, void* stream);
+                     float dropout_p, uint64_t seed, const uint64_t* seed_dev, uint32_t dropout_stream, int32_t* err_flag, void* stream);
 int dle_embed_ln_bwd(const void* dy, const void* z, const float* mean, const float* rstd, const void* gamma,
                      const int64_t* input_ids, const int64_t* token_type_ids, float* dword, float* dpos,
                      float* dtype_tab, float* part_dgamma, float* part_dbeta, int32_t B, int32_t S, int32_t H,
-                     float dropout_p, uint64_t seed, uint32_t dropout_stream, void* stream);
+                     float dropout_p, uint64_t seed, const uint64_t* seed_dev, uint32_t dropout_stream, void* stream);
 /* masked-row gather (dense sequence output): out[i,:] = x[idx[i],:]  -- bit exact.
- * replaces torch.index_select at modeling.py:590.  bwd scatters rows back (rows are unique). */
+ * replaces torch.index_select at modeling.py:590.  bwd scatters rows back (rows are unique).
+ * idx[i] == -1 marks a PADDING slot of a static-size index list (torch.nonzero_static): gather writes a zero row, scatter skips it;
+ * any other out-of-range index sets *err_flag (gather) / is skipped (scatter). */
 int dle_gather_rows(const void* x, const int64_t* idx, void* out, int64_t n_idx, int32_t H, int64_t n_rows,
                     int32_t* err_flag, void* stream);
 int dle_scatter_rows(const void* dy, const int64_t* idx, void* dx, int64_t n_idx, int32_t H, int64_t n_rows,
                      void* stream);
+/* *counter += delta on the stream (one thread): the per-step bump of a dropout `seed_dev` counter; graph-capturable */
+int dle_advance_u64(uint64_t* counter, uint64_t delta, void* stream);
 /* fp32 -> bf16 conversion (gradient tables, weight casts); bf16 -> fp32 */
 int dle_cast_f32_to_bf16(const float* x, void* y, int64_t n, void* stream);
 int dle_cast_bf16_to_f32(const void* x, float* y, int64_t n, void* stream);
@@ -201,7 +212,9 @@ typedef struct dle_lamb_group {
 int dle_lamb_plan_create(const dle_lamb_tensor* host_tensors, int32_t n_tensors, const dle_lamb_group* host_groups,
                          int32_t n_groups, int32_t grad_dtype, void** plan_out);
 int dle_lamb_plan_destroy(void* plan);
-/* re-point the plan at new grad/param addresses (same tensor count, sizes, groups); one small async H2D copy */
+/* re-point the plan at new grad/param addresses (same tensor count, sizes, groups): one small async H2D copy from a pinned staging
+ * ring owned by the plan -- no allocation and no host synchronisation on the per-step path, and legal while `stream` is being captured
+ * into a CUDA graph (at most 4 captured updates per plan: DLE_ERR_NOSYS beyond that) */
 int dle_lamb_plan_update(void* plan, const dle_lamb_tensor* host_tensors, int32_t n_tensors, void* stream);
 /* scale: device fp32 loss scale or NULL (=1).  found_inf_out / global_grad_norm_out: device fp32
  * scalars written by the call (global_grad_norm is the norm of the SCALED grads, as in the reference).

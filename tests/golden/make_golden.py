@@ -11,6 +11,10 @@ exists in NGC's patched torch.
 Outputs
   bert_tiny_golden.pt : tiny config (H=64, L=2, A=4, I=256, V=512, S=32, B=3, ragged mask):
                         state_dict, batch, per-layer activations, logits, loss, all grads.
+  bert_large2_golden.pt : the BENCHMARKED widths (BASELINE configs[1]/[2]: H=1024, A=16, I=4096, V=30528) with 2 encoder
+                        layers, B=2, ragged mask, at S=512 and S=128; bf16-representable weights regenerated from the
+                        seed by the tests; stored: loss, nsp, strided logits + per-row logsumexp over the full
+                        vocabulary, strided sequence output, every gradient norm and strided slices of selected grads.
   bert_base_golden.pt : BASELINE config 1 shape (BERT-base, B=4, S=128, fp32): params are
                         regenerated from seed by oracle.bert_oracle.init_params, so only the
                         loss, logits slices and a few grad norms are stored.
@@ -84,6 +88,14 @@ SMALL_GRAD_KEYS = ["bert.encoder.layer.0.attention.self.query.weight", "bert.enc
                    "bert.embeddings.LayerNorm.bias", "cls.predictions.transform.dense_act.weight", "bert.pooler.dense_act.weight"]
 
 
+LARGE_GRAD_KEYS = ["bert.encoder.layer.0.attention.self.query.weight", "bert.encoder.layer.0.attention.self.key.weight",
+                   "bert.encoder.layer.0.attention.self.value.bias", "bert.encoder.layer.0.attention.output.dense.weight",
+                   "bert.encoder.layer.1.intermediate.dense_act.weight", "bert.encoder.layer.1.intermediate.dense_act.bias",
+                   "bert.encoder.layer.1.output.dense.weight", "bert.encoder.layer.1.output.LayerNorm.weight",
+                   "bert.embeddings.word_embeddings.weight", "bert.embeddings.position_embeddings.weight",
+                   "cls.predictions.transform.dense_act.weight", "cls.predictions.bias", "bert.pooler.dense_act.weight"]
+
+
 def main():
     from oracle import bert_oracle as O
     modeling = import_reference_modeling()
@@ -118,6 +130,25 @@ def main():
                     grads={k: r["grads"][k].half() for k in SMALL_GRAD_KEYS}),
                os.path.join(HERE, "bert_small_golden.pt"))
     print("small loss", float(r["loss"]))
+
+    # BERT-large widths, 2 layers (the benchmarked per-layer shapes; 24 layers would only repeat them)
+    large2 = dict(O.BERT_LARGE)
+    large2.update(num_hidden_layers=2, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    sd = O.bf16_representable_params(large2, seed=77, std=0.04)
+    out = dict(cfg=large2, param_seed=77, param_std=0.04, cases={})
+    for S, P, bseed in ((512, 80, 13), (128, 20, 17)):
+        batch = O.synthetic_batch(2, S, large2["vocab_size"], P, seed=bseed, full_mask=False)
+        r = run(modeling, large2, sd, batch, capture_layers=True)
+        out["cases"][S] = dict(
+            batch_seed=bseed, max_pred=P, loss=r["loss"], nsp=r["nsp"],
+            scores_strided=r["scores"][:, ::16].half(), scores_lse=torch.logsumexp(r["scores"], -1),
+            scores_absmax=r["scores"].abs().max(),
+            seq_out_strided=r["acts"]["layer1.out"].transpose(0, 1).contiguous()[:, :, ::8].half(),
+            layer0_ctx_strided=r["acts"]["layer0.ctx"].transpose(0, 1).contiguous()[:, :, ::8].half(),
+            grad_norms={k: v.norm() for k, v in r["grads"].items()},
+            grads_strided={k: r["grads"][k].reshape(-1)[::(1 if r["grads"][k].numel() <= 4096 else 97)].clone() for k in LARGE_GRAD_KEYS})
+        print("large2 S=%d loss" % S, float(r["loss"]))
+    torch.save(out, os.path.join(HERE, "bert_large2_golden.pt"))
 
     base = dict(O.BERT_BASE)
     sd = O.init_params(base, seed=42)

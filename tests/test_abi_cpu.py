@@ -89,7 +89,8 @@ def test_version_and_argument_validation_without_a_gpu(lib):
     assert lib.dle_gemm_bf16(None, None) == -22
     args = L.GemmArgs()                       # all-null pointers, zero sizes
     assert lib.dle_gemm_bf16(ctypes.byref(args), None) == -22
-    assert lib.dle_attn_fwd(None, None, None, None, 1, 512, 16, 0, 0.0, 0, 0, None) == -22
+    assert lib.dle_attn_fwd(None, None, None, None, 1, 512, 16, 0, 0.0, 0, None, 0, None) == -22
+    assert lib.dle_advance_u64(None, 1, None) == -22
     assert lib.dle_lamb_step(None, None, 1.0, 1, 0, None, None, None, None) == -22
     assert lib.dle_gather_rows(None, None, None, 0, 0, 0, None, None) == -22
     assert lib.dle_ln_bwd_partials(65536) > 0 and lib.dle_colsum_partials(65536) > 0      # pure host helpers
