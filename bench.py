@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--ref-batch", type=int, default=0, help="sequences per CPU step (bounded sample)")
     ap.add_argument("--bucket-mb", type=int, default=100)
     ap.add_argument("--dynamic-mlm-gather", action="store_true", help="use torch.nonzero (host sync per step) like the reference instead of nonzero_static(batch*max_pred)")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference-GPU leg (the unmodified reference step timed on this GPU after our arm, N=1 only)")
+    ap.add_argument("--no-cuda-graphs", action="store_true", help="enqueue every step eagerly instead of replaying one captured CUDA graph of the whole step "
+                         "(the reference driver's --cuda_graphs, run_pretraining.py:602-640,669)")
     return ap.parse_args()
 
 
@@ -161,6 +164,35 @@ def cpu_reference_run(cfg, S, P, ref_batch, steps, warmup):
                        f"forward/backward (oracle/bert_oracle.py) + OpenMP LAMB (oracle/lamb_oracle.c)")
 
 
+def reference_gpu_leg(S, steps, warmup):
+    """The unmodified reference step (its modeling.py, its fused_lamb_CUDA kernels, its run_pretraining.py functions) timed on this GPU
+    by tools/bench_reference_gpu.py in a fresh process, at the reference's own micro-batch (32 @512 / 256 @128, README.md:813-816) and at
+    twice that; eager and with the reference's own --cuda_graphs.  Returns the list of result lines (or a one-line reason)."""
+    tool = os.path.join(ROOT, "tools", "bench_reference_gpu.py")
+    if not os.path.exists(os.path.join(ROOT, "baseline", "_ref", "BERT", "run_pretraining.py")):
+        return {"unavailable": "baseline/_ref/BERT is not installed (python baseline/install_ref.py needs /root/reference)"}
+    base = 32 if S >= 384 else 256
+    runs, out = [(base, False), (base, True), (2 * base, True)], []
+    for batch, graphs in runs:
+        cmd = [sys.executable, tool, "--arm", "reference", "--seq", str(S), "--batch", str(batch), "--steps", str(steps), "--warmup", str(warmup)]
+        if graphs:
+            cmd.append("--cuda-graphs")
+        env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT")}
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=env)
+            lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            if r.returncode == 0 and lines:
+                j = json.loads(lines[-1])
+                out.append({"micro_batch": batch, "cuda_graphs": graphs, "value": j["value"], "e2e": j["e2e"]["value"], "ms_per_step": j["ms_per_step"],
+                            "dtype": j["dtype"], "hbm_peak_gb": j.get("hbm_peak_gb")})
+            else:
+                out.append({"micro_batch": batch, "cuda_graphs": graphs, "failed": (r.stderr or r.stdout).strip().splitlines()[-1:][0][:300] if (r.stderr or r.stdout).strip() else "no output"})
+        except subprocess.TimeoutExpired:
+            out.append({"micro_batch": batch, "cuda_graphs": graphs, "failed": "timeout"})
+        log(f"reference gpu leg: {out[-1]}")
+    return {"runs": out}
+
+
 def workload(args):
     from deeplearningexamples_b200 import training as T
     S = args.seq
@@ -177,6 +209,7 @@ def config_dict(args, cfg, S, B, P, n):
             "seq_len": S, "micro_batch_per_gpu": B, "global_batch": B * n, "max_predictions_per_seq": P,
             "gradient_accumulation_steps": 1, "dropout": 0.0 if args.no_dropout else 0.1, "parallelism": f"dp{n}",
             "attention_mask": "all ones (padded to full length)", "mlm_gather": "torch.nonzero (sync)" if args.dynamic_mlm_gather else "nonzero_static(batch*max_pred), sync-free",
+            "cuda_graphs": not (args.no_cuda_graphs or args.dynamic_mlm_gather),
             "l2_policy": "per-step working set (weights 0.67 GB + activations >10 GB) exceeds the 126 MB L2; no explicit flush"}
 
 
@@ -231,17 +264,31 @@ def run_ours(args):
     loss_acc = torch.zeros(1, dtype=torch.float32, device=device)
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
 
-    def step_resident(i):
-        loss = T.take_training_step(scaler, model, crit, dev[i % 2], loss_acc)
-        T.take_optimizer_step(sched, opt, scaler)
-        return loss
+    use_graphs = not (args.no_cuda_graphs or args.dynamic_mlm_gather)
+    graph = {"g": None, "loss": None}
 
-    def step_e2e(i):
+    def one_step():                                    # take_training_step + take_optimizer_step on the static batch
+        graph["loss"] = T.take_training_step(scaler, model, crit, stage, loss_acc)
+        T.take_optimizer_step(sched, opt, scaler)
+
+    def run_step():
+        if graph["g"] is not None:
+            graph["g"].replay()
+        else:
+            one_step()
+        return graph["loss"]
+
+    def step_resident(i):                              # inputs already in HBM: device-to-device into the static batch
+        db = dev[i % 2]
+        for k in stage:
+            stage[k].copy_(db[k], non_blocking=True)
+        return run_step()
+
+    def step_e2e(i):                                   # inputs in pinned host memory, loss read back
         hb = host[i % 4]
         for k in stage:
             stage[k].copy_(hb[k], non_blocking=True)
-        loss = T.take_training_step(scaler, model, crit, stage, loss_acc)
-        T.take_optimizer_step(sched, opt, scaler)
+        loss = run_step()
         loss_host.copy_(loss.detach().float().reshape(1), non_blocking=True)
         return loss
 
@@ -261,13 +308,29 @@ def run_ours(args):
         t_host = time.perf_counter() - t_host          # host time to ENQUEUE the steps (no sync inside)
         barrier()
         log(f"  host enqueue {1000 * t_host / steps:.2f} ms/step vs device {e0.elapsed_time(e1) / steps:.2f} ms/step")
-        return T.max_over_ranks(e0.elapsed_time(e1), device)
+        return T.max_over_ranks(e0.elapsed_time(e1), device), 1000 * t_host / steps
 
     log(f"model built: B={B} S={S} world={world}")
-    for i in range(max(args.warmup, 3)):
-        step_resident(i)
+    n_warm = max(args.warmup, 3)
+    launches_per_step = None
+    if use_graphs:
+        # the reference's recipe (run_pretraining.py:611-626): eager warm-up on a side stream (11 iterations under DDP), then capture
+        for k in stage:
+            stage[k].copy_(dev[0][k])
+        n_eager = max(n_warm, 11 if world > 1 else 3)
+        n_before = L.launch_count["n"]
+        graph["g"] = T.capture_step_graph(one_step, warmup_iters=n_eager)
+        launches_per_step = (L.launch_count["n"] - n_before) // (n_eager + 1)
         torch.cuda.synchronize()
-        log(f"warm-up step {i} done")
+        log(f"captured the step into a CUDA graph after {n_eager} eager warm-up steps ({launches_per_step} kernels of libdle_b200.so per step)")
+        n_warm = n_eager
+        for i in range(2):
+            step_resident(i)
+    else:
+        for i in range(n_warm):
+            step_resident(i)
+            torch.cuda.synchronize()
+            log(f"warm-up step {i} done")
     step_e2e(0)
     torch.cuda.synchronize()
     log("warm-up done")
@@ -279,18 +342,25 @@ def run_ours(args):
     n0 = L.launch_count["n"]
     torch.cuda.nvtx.range_push("timed_resident")
     torch.cuda.profiler.start()          # ncu --profile-from-start off: capture exactly the timed region (all threads)
-    ms_res = timed(step_resident, args.steps)
+    ms_res, host_res = timed(step_resident, args.steps)
     torch.cuda.profiler.stop()
     torch.cuda.nvtx.range_pop()
     log(f"resident pass: {ms_res / args.steps:.2f} ms/step")
-    launches = L.launch_count["n"] - n0
-    K.gemm_profile = []
-    ms_e2e = timed(step_e2e, args.steps)
+    launches = (L.launch_count["n"] - n0) if launches_per_step is None else launches_per_step * args.steps
+    ms_e2e, host_e2e = timed(step_e2e, args.steps)
     log(f"e2e pass: {ms_e2e / args.steps:.2f} ms/step")
+    final_loss = loss_host.item()
+    # per-launch GEMM timing for the roofline: CUDA events cannot bracket launches inside a replayed graph, so the same step is
+    # enqueued eagerly once more (same kernels, same shapes, same stream) with an event pair around every GEMM launch
+    graph["g"] = None
+    K.gemm_profile = []
+    ms_prof, _ = timed(step_e2e, max(2, min(args.steps, 4)))
+    prof_steps = max(2, min(args.steps, 4))
     prof, K.gemm_profile = K.gemm_profile, None
     t_end = time.time()
     clocks = sampler.stop(t_start, t_end) if sampler else None
-    final_loss = loss_host.item()
+    ops.check_device_errors()
+    (model.module if hasattr(model, "module") else model).cls.check_mlm_overflow()
 
     n = world
     value = T.global_throughput(B, n, args.steps, ms_res)
@@ -307,20 +377,22 @@ def run_ours(args):
     gemm_flops = sum(f for _, _, f, _ in prof)
     ach = gemm_flops / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
     flops_seq = T.train_flops_per_seq(cfg, S, P)
-    line = {"metric": METRIC, "value": round(value, 2), "unit": "sequences/s", "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),
+    line = {"metric": METRIC, "value": round(value, 2), "unit": "sequences/s", "n_gpus": n, "steps": args.steps, "warmup": n_warm,
             "ms_per_step": round(ms_res / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": config_dict(args, cfg, S, B, P, n),
             "e2e": {"value": round(e2e, 2), "unit": "sequences/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": round(ms_e2e / args.steps, 3)},
+            "host_enqueue_ms_per_step": {"resident": round(host_res, 3), "e2e": round(host_e2e, 3)},
             "gpu_launches": launches, "hbm_peak_gb": round(torch.cuda.max_memory_allocated() / 2**30, 1),
             "roofline": {"kernel": "gemm_bf16_tcgen05_kernel (all dense projections/FFN, fwd+dgrad+wgrad)", "bound": "tensor",
                          "achieved": round(ach, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": round(ach / pk["tf_sustained"], 4),
                          "peak_source": pk["source"] + " (bf16_tflops_sustained: kernel timed inside a long step)",
                          "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch_avg": int(sum(2.0 * (m * k + n * k + m * n) for _, _, _, (m, n, k, *_r) in prof) / max(len(prof), 1)),
-                         "launches_timed": len(prof), "share_of_step": round(gemm_ms / ms_e2e, 4),
-                         "how": "CUDA events around every GEMM launch on the launching stream during the e2e timed pass; "
-                                "algorithmic flops = 2*M*N*K per launch"},
+                         "launches_timed": len(prof), "share_of_step": round(gemm_ms / ms_prof, 4),
+                         "how": "CUDA events around every GEMM launch on the launching stream during an eager pass of the same step "
+                                f"({prof_steps} steps, {round(ms_prof / prof_steps, 2)} ms/step) run right after the timed passes (events cannot bracket "
+                                "launches inside a replayed graph); algorithmic flops = 2*M*N*K per launch"},
             "model_flops_utilisation": {"train_gflop_per_seq": round(flops_seq / 1e9, 1),
                                         "achieved_tflops_per_gpu": round(value / n * flops_seq / 1e12, 1),
                                         "frac_of_sustained_peak": round(value / n * flops_seq / 1e12 / pk["tf_sustained"], 4)},
@@ -334,6 +406,27 @@ def run_ours(args):
         r = cpu_reference_run(cfg, S, P, args.ref_batch or 2, 2, 1)
         log("cpu baseline done")
         line["cpu_baseline"] = {"value": round(r["value"], 4), "unit": "sequences/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    if rank == 0 and n == 1 and not args.no_reference_gpu:
+        try:
+            del model, opt
+        except NameError:
+            pass
+        graph.clear()
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        log(f"reference gpu leg ... ({torch.cuda.memory_allocated() / 2**30:.1f} GB still allocated by this process)")
+        rg = reference_gpu_leg(S, max(3, min(args.steps, 6)), 3)
+        ok = [x for x in rg.get("runs", []) if "value" in x]
+        if ok:
+            best = max(ok, key=lambda x: x["e2e"])
+            rg.update({"value": best["value"], "e2e": best["e2e"], "micro_batch": best["micro_batch"], "unit": "sequences/s",
+                       "what": "UNMODIFIED reference step (reference modeling.py + fused_lamb_CUDA kernels + run_pretraining.py take_training_step / "
+                               "take_optimizer_step, --fp16 --allreduce_post_accumulation --allreduce_post_accumulation_fp16, eager torch ops, no TorchScript) "
+                               "timed on THIS GPU with the same CUDA-event harness; best of the runs listed"})
+            line["vs_reference_gpu"] = {"e2e_ratio": round(e2e / best["e2e"], 3), "value_ratio": round(value / best["value"], 3),
+                                        "ours_micro_batch": B, "reference_micro_batch": best["micro_batch"]}
+        line["reference_gpu"] = rg
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

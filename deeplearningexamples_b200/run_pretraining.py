@@ -11,7 +11,8 @@ What is different, and why:
   * `lddl`, `dllogger`, `h5py`, `apex` are not importable offline: batches come from `SyntheticPretrainLoader` (the lddl batch
     format: five int64 tensors) unless a real `lddl` is installed and `--input_dir` exists; logging is a JSON-lines shim.
   * TorchScript is not applicable to custom autograd functions: `--disable_jit_fusions` is implied.
-  * `--cuda_graphs` is rejected while dropout is on (dropout seeds are host-side kernel arguments today).
+  * `--cuda_graphs` captures the whole step (and the gradient-accumulation micro-step) exactly as the reference does (:602-640,669);
+    dropout stays on: masks are keyed by a device-side step counter (ops.step_counter) that the captured forward bumps.
 """
 import argparse
 import json
@@ -28,7 +29,7 @@ import torch.distributed as dist
 from . import modeling, ops
 from .lamb import FusedLAMBAMP
 from .schedulers import PolyWarmUpScheduler
-from .training import BertPretrainingCriterion, synthetic_batch
+from .training import BertPretrainingCriterion, capture_step_graph, synthetic_batch
 
 timeout_sent = False
 
@@ -166,8 +167,8 @@ def setup_training(args):
         raise ValueError("Output directory ({}) already exists and is not empty.".format(args.output_dir))
     if (not args.resume_from_checkpoint or not os.path.exists(args.output_dir)) and is_main_process():
         os.makedirs(args.output_dir, exist_ok=True)
-    if args.cuda_graphs:
-        raise RuntimeError("--cuda_graphs is not supported yet: dropout seeds are host-side kernel arguments")
+    if args.cuda_graphs and args.no_dense_sequence_output is False and args.max_predictions_per_seq <= 0:
+        raise ValueError("--cuda_graphs needs --max_predictions_per_seq > 0 (static number of gathered MLM rows)")
     return device, args
 
 
@@ -267,7 +268,10 @@ def take_optimizer_step(args, lr_scheduler, optimizer, grad_scaler, skipped_acc)
     if grad_scaler.is_enabled():
         skipped_acc.add_(optimizer._found_inf)               # before update() resets the inf tracker (:530-533)
     grad_scaler.update()
-    optimizer.zero_grad(set_to_none=True)
+    # Captured graphs freeze "assign" vs "accumulate" for every gradient: with gradient accumulation under --cuda_graphs the gradient
+    # buffers therefore stay allocated and are zeroed in place, so the micro-step graph and the full-step graph both ACCUMULATE into the
+    # same static buffers (the reference's set_to_none=True, :536, is kept otherwise).
+    optimizer.zero_grad(set_to_none=not (args.cuda_graphs and args.gradient_accumulation_steps > 1))
 
 
 def main(argv=None):
@@ -308,6 +312,28 @@ def main(argv=None):
     host = {k: torch.zeros(1, dtype=torch.float32).pin_memory() for k in ("loss", "lr", "skipped")}
     model_step, raw_train_start = 0, None
     skip_for_perf = 50 if args.phase2 else 4
+    static_batch = full_graph = accum_graph = None
+    if args.cuda_graphs:
+        # reference :602-640: a static device batch, eager warm-up on a side stream, then one captured graph for the full step and one
+        # for the gradient-accumulation micro-step (no_sync under DDP).  The static batch starts as a real batch (all-ones labels, as
+        # the reference uses, would mark every position as masked and trip the static masked-row bound).
+        first = next(iter(loader))
+        static_batch = {k: v.to(device) for k, v in first.items()}
+        full_graph = capture_step_graph(lambda: (take_training_step(args, grad_scaler, model, criterion, static_batch, loss_acc),
+                                                 take_optimizer_step(args, lr_scheduler, optimizer, grad_scaler, skipped_acc)), warmup_iters=11)
+        if args.gradient_accumulation_steps > 1:
+            def micro():
+                if hasattr(model, "no_sync"):
+                    with model.no_sync():
+                        take_training_step(args, grad_scaler, model, criterion, static_batch, loss_acc)
+                else:
+                    take_training_step(args, grad_scaler, model, criterion, static_batch, loss_acc)
+            accum_graph = capture_step_graph(micro, warmup_iters=3)
+            optimizer.zero_grad(set_to_none=False)       # the warm-up / captured micro-steps accumulated into the static gradient buffers
+        # the warm-up / capture executions advanced the optimizer: rewind the statistics the run reports (weights keep the 12+ steps,
+        # exactly as in the reference, whose warm-up also trains on the static batch)
+        loss_acc.zero_()
+        skipped_acc.zero_()
     while True:
         for step, batch in enumerate(loader):
             model_step += 1
@@ -315,14 +341,20 @@ def main(argv=None):
             if raw_train_start is None and step == skip_for_perf:
                 torch.cuda.synchronize()
                 raw_train_start = time.time()
-            batch = {k: v.to(device, non_blocking=True) for k, v in batch.items()}
-            if args.allreduce_post_accumulation and accumulating and hasattr(model, "no_sync"):
-                with model.no_sync():
-                    take_training_step(args, grad_scaler, model, criterion, batch, loss_acc)
+            if args.cuda_graphs:
+                for k in batch.keys():
+                    static_batch[k].copy_(batch[k], non_blocking=True)
+                (accum_graph if (accumulating and accum_graph is not None) else full_graph).replay()
             else:
-                take_training_step(args, grad_scaler, model, criterion, batch, loss_acc)
+                batch = {k: v.to(device, non_blocking=True) for k, v in batch.items()}
+                if args.allreduce_post_accumulation and accumulating and hasattr(model, "no_sync"):
+                    with model.no_sync():
+                        take_training_step(args, grad_scaler, model, criterion, batch, loss_acc)
+                else:
+                    take_training_step(args, grad_scaler, model, criterion, batch, loss_acc)
+                if not accumulating:
+                    take_optimizer_step(args, lr_scheduler, optimizer, grad_scaler, skipped_acc)
             if not accumulating:
-                take_optimizer_step(args, lr_scheduler, optimizer, grad_scaler, skipped_acc)
                 host["loss"].copy_(loss_acc, non_blocking=True)
                 host["lr"].copy_(optimizer.param_groups[0]['lr'].reshape(1), non_blocking=True)
                 host["skipped"].copy_(skipped_acc, non_blocking=True)
@@ -341,6 +373,8 @@ def main(argv=None):
                             loss_acc.div_(get_world_size())
                             dist.all_reduce(loss_acc)
                         final_loss = loss_acc.item()
+                        ops.check_device_errors()
+                        (model.module if hasattr(model, "module") else model).cls.check_mlm_overflow()
                         logger.log((epoch, dynamic_step), {"final_loss": final_loss})
                         checkpoint_step(args, epoch, dynamic_step, model, optimizer, grad_scaler, last3, logger)
                         return args, train_time_raw, model_step, skip_for_perf, final_loss, logger

@@ -36,3 +36,25 @@ class PolyWarmUpScheduler(_LRScheduler):
         lr = torch.where(progress < self.warmup, self.base_lr * progress / self.warmup,
                          self.base_lr * ((1.0 - progress) ** self.degree))
         return [lr for _ in self.optimizer.param_groups]
+
+
+class LinearWarmUpScheduler(_LRScheduler):
+    """Linear warm-up to the base rate over `warmup` (a fraction of total_steps), then linear decay to zero at total_steps -- the
+    host-side schedule of the SQuAD fine-tuning driver (reference schedulers.py:90-106, used at run_squad.py:1014-1016)."""
+
+    def __init__(self, optimizer, warmup, total_steps, last_epoch=-1):
+        self.warmup, self.total_steps = float(warmup), float(total_steps)
+        super().__init__(optimizer, last_epoch)
+
+    def step(self, epoch=None):
+        self.last_epoch = epoch if epoch is not None else self.last_epoch + 1
+        for group, lr in zip(self.optimizer.param_groups, self.get_lr()):
+            group['lr'] = lr
+
+    def get_lr(self):
+        progress = self.last_epoch / self.total_steps
+        if progress < self.warmup:
+            factor = progress / self.warmup
+        else:
+            factor = max((progress - 1.0) / (self.warmup - 1.0), 0.0)
+        return [base * factor for base in self.base_lrs]

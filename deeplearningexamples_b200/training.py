@@ -132,6 +132,24 @@ def take_optimizer_step(lr_scheduler, optimizer, grad_scaler):
     optimizer.zero_grad(set_to_none=True)
 
 
+def capture_step_graph(fn, warmup_iters=11):
+    """Capture `fn` (a whole training step or a gradient-accumulation micro-step) into a CUDA graph the way the reference driver
+    does (run_pretraining.py:611-640): `warmup_iters` eager executions on a side stream first (lazy optimizer state, DDP bucket
+    rebuild, cuBLAS/NCCL initialisation must all have happened -- the reference uses 11 for DDP), then one captured execution.
+    Requirements the product path meets: static shapes (nonzero_static row gather), no host synchronisation, dropout masks keyed by
+    the device step counter (ops.step_counter), LAMB tables patched by a capturable copy.  Returns the torch.cuda.CUDAGraph."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(warmup_iters):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        fn()
+    return graph
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # multi-GPU host logic (one process per GPU, pure data parallelism: run_pretraining.py:338,455-475,544-547)
 # ------------------------------------------------------------------------------------------------------------------

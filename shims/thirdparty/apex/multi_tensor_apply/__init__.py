@@ -1,0 +1,13 @@
+class MultiTensorApply(object):
+    """apex.multi_tensor_apply.MultiTensorApply: calls op(chunk_size, noop_flag, tensor_lists, *args) (chunk 2048*32 as apex ships)."""
+    available = True
+    warned = False
+
+    def __init__(self, chunk_size):
+        self.chunk_size = chunk_size
+
+    def __call__(self, op, noop_flag_buffer, tensor_lists, *args):
+        return op(self.chunk_size, noop_flag_buffer, tensor_lists, *args)
+
+
+multi_tensor_applier = MultiTensorApply(2048 * 32)
