@@ -29,10 +29,12 @@ def _rank_world(local_rank):
     return int(os.environ.get("RANK", max(local_rank, 0))), int(os.environ.get("WORLD_SIZE", 1))
 
 
-def _synth_samples(n, seq_len, max_pred, vocab, seed):
-    """n samples with lengths ~ U{seq_len/4 .. seq_len}: dicts of python lists in the parquet schema."""
+def _synth_samples(n, seq_len, max_pred, vocab, seed, len_seed=None):
+    """n samples with lengths ~ U{seq_len/4 .. seq_len}: dicts of python lists in the parquet schema.  The LENGTHS come from `len_seed`
+    (rank-independent: every rank then holds equally populated bins, as LDDL's balanced shards do), the tokens from `seed`."""
+    gl = torch.Generator().manual_seed(seed if len_seed is None else len_seed)
+    lens = torch.randint(max(seq_len // 4, 8), seq_len + 1, (n,), generator=gl).tolist()
     g = torch.Generator().manual_seed(seed)
-    lens = torch.randint(max(seq_len // 4, 8), seq_len + 1, (n,), generator=g).tolist()
     out = []
     for L in lens:
         la = max(3, L // 2)
@@ -70,9 +72,10 @@ def _collate(samples, pad_to, pin):
 
 
 class BertPretrainBinnedLoader:
-    def __init__(self, bins, seq_len, bin_size, batch_size, base_seed, start_epoch, pin):
-        """bins: {bin index -> list of this rank's samples}."""
+    def __init__(self, bins, seq_len, bin_size, batch_size, base_seed, start_epoch, pin, bin_weights=None):
+        """bins: {bin index -> list of this rank's samples}; bin_weights: {bin index -> GLOBAL population} (identical on every rank)."""
         self.bins = {k: v for k, v in bins.items() if len(v) > 0}
+        self.bin_weights = bin_weights
         self.seq_len, self.bin_size, self.batch_size = seq_len, bin_size, batch_size
         self.base_seed, self.epoch, self.pin = base_seed, start_epoch, pin
         total = sum(len(v) for v in self.bins.values())
@@ -87,7 +90,7 @@ class BertPretrainBinnedLoader:
 
     def __iter__(self):
         keys = sorted(self.bins)
-        weights = torch.tensor([float(len(self.bins[k])) for k in keys])
+        weights = torch.tensor([float((self.bin_weights or {}).get(k, len(self.bins[k]))) for k in keys])
         g = torch.Generator().manual_seed(self.base_seed * 1000003 + self.epoch)       # same on every rank: same bin sequence
         cursor = {k: 0 for k in keys}
         for step in range(self._len):
@@ -126,11 +129,12 @@ def get_bert_pretrain_data_loader(path, local_rank=0, shuffle_buffer_size=16384,
     batch_size = int(kw.get("batch_size", 32))
     pin = bool(kw.get("pin_memory", False))
     rank, world = _rank_world(local_rank)
-    bins = {}
+    bins, weights = {}, None
     if path is not None and os.path.isdir(str(path)) and os.path.exists(os.path.join(str(path), "meta.json")):
         import pyarrow.parquet as pq
         meta = json.load(open(os.path.join(path, "meta.json")))
         seq_len, bin_size = int(meta["seq_len"]), int(meta.get("bin_size", 0))
+        weights = {int(k): float(v) for k, v in meta.get("bin_counts", {}).items()} or None
         for d in sorted(os.listdir(path)):
             if not d.startswith("bin_"):
                 continue
@@ -145,8 +149,8 @@ def get_bert_pretrain_data_loader(path, local_rank=0, shuffle_buffer_size=16384,
         o = _parse_spec(str(path or "synthetic"))
         seq_len, bin_size = o["seq_len"], o["bin_size"]
         per_rank = max(batch_size, o["samples"] // world)
-        for s in _synth_samples(per_rank, seq_len, o["max_pred"], o["vocab"], seed=base_seed + 7919 * rank):
+        for s in _synth_samples(per_rank, seq_len, o["max_pred"], o["vocab"], seed=base_seed + 7919 * rank + 1, len_seed=base_seed):
             L = len(s["a_ids"]) + len(s["b_ids"])
             k = 0 if bin_size <= 0 else (L - 1) // bin_size
             bins.setdefault(k, []).append(s)
-    return BertPretrainBinnedLoader(bins, seq_len, bin_size, batch_size, int(base_seed), int(start_epoch), pin)
+    return BertPretrainBinnedLoader(bins, seq_len, bin_size, batch_size, int(base_seed), int(start_epoch), pin, bin_weights=weights)
