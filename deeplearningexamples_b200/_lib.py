@@ -60,6 +60,8 @@ SIGNATURES = {
     "dle_gather_rows": (_i32, [_vp, _vp, _vp, _i64, _i32, _i64, _vp, _vp]),
     "dle_scatter_rows": (_i32, [_vp, _vp, _vp, _i64, _i32, _i64, _vp]),
     "dle_advance_u64": (_i32, [_vp, _u64, _vp]),
+    "dle_softmax_ce_fwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _i64, _i64, _vp, _vp]),
+    "dle_softmax_ce_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i64, _i64, _i64, _vp]),
     "dle_cast_f32_to_bf16": (_i32, [_vp, _vp, _i64, _vp]),
     "dle_cast_bf16_to_f32": (_i32, [_vp, _vp, _i64, _vp]),
     "dle_lamb_plan_create": (_i32, [ctypes.POINTER(LambTensor), _i32, ctypes.POINTER(LambGroup), _i32, _i32,

@@ -237,6 +237,29 @@ def scatter_rows(dy, idx, n_rows):
     return dx
 
 
+def softmax_ce_fwd(logits, labels, ignore_index=-1, err_flag=None):
+    """fp32 log-sum-exp and per-row loss of bf16 logits [rows, V]; returns (lse [rows], loss_rows [rows]) fp32."""
+    lib = L.load()
+    _req(logits, bf16, "logits"); _req(labels, torch.int64, "labels")
+    rows, V = logits.shape
+    ld = _row_major_2d(logits, "logits")
+    lse = torch.empty(rows, device=logits.device, dtype=torch.float32)
+    loss = torch.empty(rows, device=logits.device, dtype=torch.float32)
+    L.launch_count["n"] += 1; L.check(lib.dle_softmax_ce_fwd(_ptr(logits), _ptr(labels), _ptr(lse), _ptr(loss), rows, V, ld, ignore_index, _ptr(err_flag), _stream()),
+                                      "dle_softmax_ce_fwd")
+    return lse, loss
+
+
+def softmax_ce_bwd(logits, labels, lse, grad_scale, ignore_index=-1):
+    """dlogits (bf16, same shape) = (softmax - onehot) * grad_scale for counted rows; grad_scale: fp32 device scalar."""
+    lib = L.load()
+    rows, V = logits.shape
+    out = torch.empty((rows, V), device=logits.device, dtype=bf16)
+    L.launch_count["n"] += 1; L.check(lib.dle_softmax_ce_bwd(_ptr(logits), _ptr(labels), _ptr(lse), _ptr(_req(grad_scale, torch.float32, "grad_scale")), _ptr(out), rows, V,
+                                                            _row_major_2d(logits, "logits"), V, ignore_index, _stream()), "dle_softmax_ce_bwd")
+    return out
+
+
 def advance_u64(counter, delta=1):
     """counter (int64/uint64 device tensor, 1 element) += delta on the current stream; graph-capturable."""
     lib = L.load()

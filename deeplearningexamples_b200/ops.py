@@ -364,3 +364,24 @@ class GatherRowsFn(torch.autograd.Function):
     def backward(ctx, dy):
         (idx,) = ctx.saved_tensors
         return K.scatter_rows(dy.contiguous(), idx, ctx.n_rows), None
+
+
+# -------------------------------------------------------------------------------------------------
+# mean cross-entropy over the vocabulary on bf16 logits, fp32 arithmetic, no fp32 copy of the logits
+# replaces CrossEntropyLoss(ignore_index=-1) on the MLM scores (run_pretraining.py:85-95)
+# -------------------------------------------------------------------------------------------------
+class SoftmaxCrossEntropyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, ignore_index):
+        x = logits if logits.stride(-1) == 1 else logits.contiguous()
+        lse, loss_rows = K.softmax_ce_fwd(x, labels, ignore_index, err_flag=err_flag(x.device))
+        count = (labels != ignore_index).sum().to(torch.float32)
+        ctx.save_for_backward(x, labels, lse, count)
+        ctx.ignore_index = ignore_index
+        return loss_rows.sum() / count
+
+    @staticmethod
+    def backward(ctx, g):
+        x, labels, lse, count = ctx.saved_tensors
+        scale = (g.to(torch.float32) / count).reshape(1).contiguous()
+        return K.softmax_ce_bwd(x, labels, lse, scale, ctx.ignore_index), None, None

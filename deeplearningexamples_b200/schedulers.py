@@ -40,13 +40,32 @@ class PolyWarmUpScheduler(_LRScheduler):
 
 class LinearWarmUpScheduler(_LRScheduler):
     """Linear warm-up to the base rate over `warmup` (a fraction of total_steps), then linear decay to zero at total_steps -- the
-    host-side schedule of the SQuAD fine-tuning driver (reference schedulers.py:90-106, used at run_squad.py:1014-1016)."""
+    schedule of the SQuAD fine-tuning driver (reference schedulers.py:90-106, used at run_squad.py:1014-1016).
+    Host-side by default, like the reference.  With `device` set the schedule is evaluated on the device from the optimizer's own
+    step counter (as PolyWarmUpScheduler does), writing the lr tensor in place: no host value is baked into a captured CUDA graph."""
 
-    def __init__(self, optimizer, warmup, total_steps, last_epoch=-1):
+    def __init__(self, optimizer, warmup, total_steps, last_epoch=-1, device=None, base_lr=None):
         self.warmup, self.total_steps = float(warmup), float(total_steps)
+        self.device = device
+        if device is not None:
+            self._base = torch.tensor(float(base_lr if base_lr is not None else 1.0), device=device)
         super().__init__(optimizer, last_epoch)
 
     def step(self, epoch=None):
+        if self.device is not None:
+            group0 = self.optimizer.param_groups[0]
+            step_t = group0['step'] if isinstance(group0.get('step'), torch.Tensor) else torch.zeros(1, dtype=torch.int32, device=self.device)
+            progress = (step_t.reshape(()).float() + 1.0) / self.total_steps
+            factor = torch.where(progress < self.warmup, progress / self.warmup,
+                                 torch.clamp((progress - 1.0) / (self.warmup - 1.0), min=0.0))
+            lr = self._base * factor
+            for group in self.optimizer.param_groups:
+                cur = group.get('lr')
+                if isinstance(cur, torch.Tensor) and cur.is_cuda and cur.dtype == torch.float32 and cur.dim() == 0:
+                    cur.copy_(lr)
+                else:
+                    group['lr'] = lr.clone()
+            return
         self.last_epoch = epoch if epoch is not None else self.last_epoch + 1
         for group, lr in zip(self.optimizer.param_groups, self.get_lr()):
             group['lr'] = lr

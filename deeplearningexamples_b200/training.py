@@ -14,7 +14,7 @@ Differences: bf16 instead of fp16 (`model.bfloat16()` where the reference does `
 """
 import torch
 
-from . import modeling
+from . import modeling, ops
 from .lamb import FusedLAMBAMP
 from .schedulers import PolyWarmUpScheduler
 
@@ -38,11 +38,17 @@ class BertPretrainingCriterion(torch.nn.Module):
         self.loss_fn = torch.nn.CrossEntropyLoss(ignore_index=-1)
         self.vocab_size = vocab_size
         self.sequence_output_is_dense = sequence_output_is_dense
+        self.fused_ce = True
 
     def forward(self, prediction_scores, seq_relationship_score, masked_lm_labels, next_sentence_labels):
         # cross-entropy runs in fp32 on the bf16 logits, as it does under the reference's autocast (CE is on autocast's fp32 list;
-        # run_pretraining.py:519-522)
-        scores = prediction_scores.view(-1, self.vocab_size).float()
+        # run_pretraining.py:519-522).  CUDA bf16 logits take the fused kernel (fp32 arithmetic in registers, no fp32 copy of the
+        # [rows, V] tensor: ops.SoftmaxCrossEntropyFn); anything else goes through torch on an fp32 copy.
+        scores = prediction_scores.view(-1, self.vocab_size)
+        fused = self.fused_ce and scores.is_cuda and scores.dtype == torch.bfloat16 and self.vocab_size % 8 == 0 and self.vocab_size <= 32768
+        if not fused:
+            scores = scores.float()
+        mlm_loss_fn = (lambda sc, lab: ops.SoftmaxCrossEntropyFn.apply(sc, lab, -1)) if fused else self.loss_fn
         if self.sequence_output_is_dense:
             # reference: labels[labels != -1] (boolean indexing => host sync).  Same rows, same order, without the sync: the
             # first `n` non-ignored positions, n = rows of the (already dense) prediction scores; surplus slots (static-count
@@ -50,9 +56,9 @@ class BertPretrainingCriterion(torch.nn.Module):
             flat = masked_lm_labels.view(-1)
             idx = torch.nonzero_static(flat != -1, size=scores.shape[0], fill_value=-1).squeeze(-1)
             mlm_labels = torch.where(idx >= 0, flat[idx.clamp_min(0)], torch.full_like(idx, -1))
-            masked_lm_loss = self.loss_fn(scores, mlm_labels)
+            masked_lm_loss = mlm_loss_fn(scores, mlm_labels)
         else:
-            masked_lm_loss = self.loss_fn(scores, masked_lm_labels.view(-1))
+            masked_lm_loss = mlm_loss_fn(scores, masked_lm_labels.view(-1))
         next_sentence_loss = self.loss_fn(seq_relationship_score.view(-1, 2).float(), next_sentence_labels.view(-1))
         return masked_lm_loss + next_sentence_loss
 

@@ -173,6 +173,21 @@ int dle_gather_rows(const void* x, const int64_t* idx, void* out, int64_t n_idx,
                     int32_t* err_flag, void* stream);
 int dle_scatter_rows(const void* dy, const int64_t* idx, void* dx, int64_t n_idx, int32_t H, int64_t n_rows,
                      void* stream);
+/* ------------------------------------------------------------------------------------------
+ * Softmax cross-entropy over the vocabulary on bf16 logits, fp32 arithmetic, one pass per direction (HBM-bound).
+ * replaces: CrossEntropyLoss(ignore_index=-1) on the MLM prediction scores, run_pretraining.py:85-95 (under the reference's autocast:
+ *   an fp32 copy of the [rows, V] logits + log_softmax + nll_loss and their backward).
+ *   fwd: lse[r] = logsumexp_v logits[r,v]; loss_rows[r] = lse[r] - logits[r, labels[r]], 0 where labels[r] == ignore_index.
+ *        (mean loss = sum(loss_rows) / #counted rows: two tiny reductions left to the caller).  A label outside [0,V) that is
+ *        not ignore_index sets *err_flag (may be NULL).  V % 8 == 0, V <= 32768.
+ *   bwd: dlogits[r,v] = (softmax(logits[r])[v] - [v == labels[r]]) * *grad_scale for counted rows, 0 otherwise; grad_scale is a DEVICE
+ *        fp32 scalar (dLoss / #counted rows) so no host value is needed.  dlogits may alias logits.
+ * ------------------------------------------------------------------------------------------ */
+int dle_softmax_ce_fwd(const void* logits, const int64_t* labels, float* lse, float* loss_rows, int64_t rows, int32_t V,
+                       int64_t ld, int64_t ignore_index, int32_t* err_flag, void* stream);
+int dle_softmax_ce_bwd(const void* logits, const int64_t* labels, const float* lse, const float* grad_scale, void* dlogits,
+                       int64_t rows, int32_t V, int64_t ld, int64_t ld_d, int64_t ignore_index, void* stream);
+
 /* *counter += delta on the stream (one thread): the per-step bump of a dropout `seed_dev` counter; graph-capturable */
 int dle_advance_u64(uint64_t* counter, uint64_t delta, void* stream);
 /* fp32 -> bf16 conversion (gradient tables, weight casts); bf16 -> fp32 */
