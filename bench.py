@@ -35,7 +35,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--seq", type=int, default=512, help="512 = phase 2 (headline), 128 = phase 1")
+    ap.add_argument("--workload", default="pretrain", choices=["pretrain", "squad"], help="pretrain = BERT-large pretraining step (headline); squad = SQuAD fine-tuning "
+                         "step, seq 384, QA head, FusedAdam + clip (BASELINE.json configs[3])")
+    ap.add_argument("--seq", type=int, default=0, help="0 = 512 (phase 2, headline) for pretrain / 384 for squad; 128 = phase 1")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU micro-batch (0 = 128 @512, 512 @128 -- 65536 tokens per GPU per step; the reference ran 32 @512 / 256 @128 on 80 GB "
                          "A100s, SURVEY.md 8d; 180 GB fits 4x that and the LAMB / allreduce cost per sequence halves again vs 64)")
     ap.add_argument("--max-pred", type=int, default=0)
@@ -195,7 +197,11 @@ def reference_gpu_leg(S, steps, warmup):
 
 def workload(args):
     from deeplearningexamples_b200 import training as T
-    S = args.seq
+    if args.workload == "squad":
+        cfg = dict(T.BERT_LARGE)
+        cfg["vocab_size"] = 30528
+        return cfg, args.seq or 384, args.batch or 32, 0          # reference micro-batch 32 at seq 384 (README.md:841-842)
+    S = args.seq or 512
     B = args.batch or (128 if S >= 384 else 512)
     P = args.max_pred or (80 if S >= 384 else 20)
     cfg = dict(T.BERT_LARGE)
@@ -204,6 +210,12 @@ def workload(args):
 
 
 def config_dict(args, cfg, S, B, P, n):
+    if args.workload == "squad":
+        return {"workload": f"BERT-large SQuAD fine-tuning step seq{S} bf16 FusedAdam + global-norm clip (BASELINE.json configs[3] per-GPU shape)",
+                "seq_len": S, "micro_batch_per_gpu": B, "global_batch": B * n, "gradient_accumulation_steps": 1,
+                "dropout": 0.0 if args.no_dropout else 0.1, "parallelism": f"dp{n}", "attention_mask": "all ones (padded to full length)",
+                "cuda_graphs": not args.no_cuda_graphs,
+                "l2_policy": "per-step working set (weights 0.67 GB + activations) exceeds the 126 MB L2; no explicit flush"}
     phase = "phase-2" if S >= 384 else "phase-1"
     return {"workload": f"BERT-large {phase} pretraining step seq{S} bf16 LAMB (BASELINE.json configs[{2 if S >= 384 else 1}] per-GPU shape)",
             "seq_len": S, "micro_batch_per_gpu": B, "global_batch": B * n, "max_predictions_per_seq": P,
@@ -254,10 +266,17 @@ def run_ours(args):
     if args.no_dropout:
         cfg["hidden_dropout_prob"] = cfg["attention_probs_dropout_prob"] = 0.0
     ops.manual_seed(42 + rank)
-    model, opt, scaler, sched, crit, _ = T.prepare_model_and_optimizer(cfg, device, distributed=world > 1, bucket_cap_mb=args.bucket_mb,
-                                                                      seed=42, static_masked_count=None if args.dynamic_mlm_gather else B * P)
+    squad = args.workload == "squad"
+    if squad:
+        from deeplearningexamples_b200 import squad as SQ
+        model, opt, sched = SQ.prepare_squad_model_and_optimizer(cfg, device, distributed=world > 1, seed=42, total_steps=10000)
+        scaler = crit = None
+        host = [SQ.synthetic_squad_batch(B, S, cfg["vocab_size"], seed=T.rank_seed(42, rank) + 100 * i, pin=True) for i in range(4)]
+    else:
+        model, opt, scaler, sched, crit, _ = T.prepare_model_and_optimizer(cfg, device, distributed=world > 1, bucket_cap_mb=args.bucket_mb,
+                                                                          seed=42, static_masked_count=None if args.dynamic_mlm_gather else B * P)
+        host = [T.synthetic_batch(B, S, cfg["vocab_size"], P, seed=T.rank_seed(42, rank) + 100 * i, pin=True) for i in range(4)]
     model.train()
-    host = [T.synthetic_batch(B, S, cfg["vocab_size"], P, seed=T.rank_seed(42, rank) + 100 * i, pin=True) for i in range(4)]
     dev = [{k: v.to(device) for k, v in hb.items()} for hb in host[:2]]
     stage = {k: torch.empty_like(v, device=device) for k, v in host[0].items()}
     loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
@@ -268,6 +287,9 @@ def run_ours(args):
     graph = {"g": None, "loss": None}
 
     def one_step():                                    # take_training_step + take_optimizer_step on the static batch
+        if squad:
+            graph["loss"] = SQ.squad_training_step(model, opt, sched, stage, loss_acc)
+            return
         graph["loss"] = T.take_training_step(scaler, model, crit, stage, loss_acc)
         T.take_optimizer_step(sched, opt, scaler)
 
@@ -360,7 +382,8 @@ def run_ours(args):
     t_end = time.time()
     clocks = sampler.stop(t_start, t_end) if sampler else None
     ops.check_device_errors()
-    (model.module if hasattr(model, "module") else model).cls.check_mlm_overflow()
+    if not squad:
+        (model.module if hasattr(model, "module") else model).cls.check_mlm_overflow()
 
     n = world
     value = T.global_throughput(B, n, args.steps, ms_res)
@@ -376,7 +399,7 @@ def run_ours(args):
     gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof)
     gemm_flops = sum(f for _, _, f, _ in prof)
     ach = gemm_flops / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
-    flops_seq = T.train_flops_per_seq(cfg, S, P)
+    flops_seq = SQ.squad_flops_per_seq(cfg, S) if squad else T.train_flops_per_seq(cfg, S, P)
     line = {"metric": METRIC, "value": round(value, 2), "unit": "sequences/s", "n_gpus": n, "steps": args.steps, "warmup": n_warm,
             "ms_per_step": round(ms_res / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": config_dict(args, cfg, S, B, P, n),
@@ -399,14 +422,14 @@ def run_ours(args):
             "final_loss": round(final_loss, 4)}
     if clocks is not None:
         line["clocks"] = clocks
-    if rank == 0 and n == 1 and not args.no_cpu_baseline:
+    if rank == 0 and n == 1 and not args.no_cpu_baseline and not squad:
         del model, opt
         torch.cuda.empty_cache()
         log("cpu baseline ...")
         r = cpu_reference_run(cfg, S, P, args.ref_batch or 2, 2, 1)
         log("cpu baseline done")
         line["cpu_baseline"] = {"value": round(r["value"], 4), "unit": "sequences/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
-    if rank == 0 and n == 1 and not args.no_reference_gpu:
+    if rank == 0 and n == 1 and not args.no_reference_gpu and not squad:
         try:
             del model, opt
         except NameError:

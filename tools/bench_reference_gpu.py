@@ -70,7 +70,7 @@ def main():
         json.dump(cfg, open(cfg_path, "w"))
     out_dir = f"/tmp/refbench_{os.getpid()}"
     argv = [script, "--input_dir", f"synthetic?seq_len={a.seq}&max_pred={P}&samples={4 * a.batch * world}", "--config_file", cfg_path,
-            "--output_dir", out_dir, "--train_batch_size", str(a.batch), "--max_seq_length", str(a.seq), "--max_predictions_per_seq", str(P),
+            "--output_dir", out_dir, "--vocab_file", "vocab.txt", "--train_batch_size", str(a.batch), "--max_seq_length", str(a.seq), "--max_predictions_per_seq", str(P),
             "--max_steps", "7038", "--warmup_proportion", "0.128", "--learning_rate", "4e-3", "--seed", "42", "--do_train", "--skip_checkpoint",
             "--json-summary", os.path.join(out_dir, "dllogger.json"), "--fp16"]
     if a.mode == "fp16":
