@@ -396,6 +396,15 @@ def run_ours(args):
         traffic, traffic_src = tj["avg_dram_traffic_bytes_per_launch"], (
             "profiles/r01_gemm_traffic.json (ncu --set full, 12 forward GEMM launches of this command; the same 12 launches move "
             f"{tj.get('avg_algorithmic_bytes_per_launch', 0)} algorithmic bytes on average -- algorithmic_bytes_per_launch_avg below averages ALL timed launches)")
+    by_shape = {}
+    for a_, b_, f_, tag in prof:
+        d = by_shape.setdefault(tag, [0, 0.0, 0.0])
+        d[0] += 1; d[1] += a_.elapsed_time(b_); d[2] += f_
+    epi_names = ["bias", "bias_gelu", "bias_dropout_residual", "dgelu", "add", "atomic_f32", "f32", "bias_tanh"]
+    gemm_table = sorted(({"M": t[0], "N": t[1], "K": t[2], "a_mn": t[3], "b_mn": t[4], "epilogue": epi_names[t[5]], "launches": d[0],
+                          "ms_total": round(d[1], 3), "tflops": round(d[2] / d[1] / 1e9, 1)} for t, d in by_shape.items()), key=lambda r: -r["ms_total"])
+    for row in gemm_table[:24]:
+        log(f"  gemm {row}")
     gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof)
     gemm_flops = sum(f for _, _, f, _ in prof)
     ach = gemm_flops / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
@@ -412,10 +421,12 @@ def run_ours(args):
                          "peak_source": pk["source"] + " (bf16_tflops_sustained: kernel timed inside a long step)",
                          "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch_avg": int(sum(2.0 * (m * k + n * k + m * n) for _, _, _, (m, n, k, *_r) in prof) / max(len(prof), 1)),
-                         "launches_timed": len(prof), "share_of_step": round(gemm_ms / ms_prof, 4),
+                         "launches_timed": len(prof), "share_of_step": round((gemm_ms / prof_steps) / (ms_e2e / args.steps), 4),
+                         "by_shape_top": gemm_table[:12],
                          "how": "CUDA events around every GEMM launch on the launching stream during an eager pass of the same step "
-                                f"({prof_steps} steps, {round(ms_prof / prof_steps, 2)} ms/step) run right after the timed passes (events cannot bracket "
-                                "launches inside a replayed graph); algorithmic flops = 2*M*N*K per launch"},
+                                f"({prof_steps} steps, {round(ms_prof / prof_steps, 2)} ms/step incl. the host cost of recording two events per launch) run right after the "
+                                "timed passes (events cannot bracket launches inside a replayed graph); algorithmic flops = 2*M*N*K per launch; "
+                                "share_of_step = GEMM ms per step of that pass / ms per step of the timed e2e pass"},
             "model_flops_utilisation": {"train_gflop_per_seq": round(flops_seq / 1e9, 1),
                                         "achieved_tflops_per_gpu": round(value / n * flops_seq / 1e12, 1),
                                         "frac_of_sustained_peak": round(value / n * flops_seq / 1e12 / pk["tf_sustained"], 4)},

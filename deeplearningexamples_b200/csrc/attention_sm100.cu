@@ -313,14 +313,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdParam
 }
 
 // =================================================================================================
-// backward
+// backward  (v4)
+//   CTA   : one (batch, head); loops kv tiles j (outer) x query tiles i (inner), pair index t = j*n + i.
+//   smem  : K_j, V_j 32 KB + Q_i, dO_i of ALL query tiles resident (<= 128 KB, loaded once per head) + P~ 32 KB + dS 32 KB + mask
+//           = 226.3 KB at S = 512 (one CTA per SM).
+//   TMEM  : dQ of all query tiles 4 x 64 | dK 64 | dV 64 | S half 64 | dP half 64 = 512 columns: every accumulator stays on chip
+//           (no atomics, no scratch in HBM, deterministic), and S / dP are produced 64 KEY COLUMNS AT A TIME so that they fit beside them.
+//   warps : 0 = TMA producer, 1 = MMA issuer, 2..17 = two compute groups of 8 warps: group g owns key half g of every pair
+//           (thread = one query row x 32 keys).  The groups run half a pair apart, so while one computes P / dS from registers the
+//           tensor core produces the other's S / dP: v3 measured no gain from overlapping whole-tile phases because its dQ went through
+//           16 B/clk/SM of L2 atomics; v1 kept dQ on chip but had S and dP share columns, serialising every MMA behind a compute phase.
+//   early release : a TMEM buffer is handed back (s_free / dp_free) as soon as its columns are in registers, not after they are used.
+//   MMA order per pair : S(t,0) dP(t,0) S(t,1) dV(t-1) dP(t,1) dK(t-1) dQ(t-1) -- the accumulating MMAs trail by one pair, so the issuer
+//           never blocks the next pair's S / dP behind operands (P~, dS) that the compute warps are still writing.
 // =================================================================================================
 constexpr int BWD_THREADS = 576;       // warp 0: TMA + TMEM alloc, warp 1: MMA, warps 2..17: compute
-constexpr int BWD_COMPUTE_THREADS = 512;   // 4 warps per TMEM lane quarter, each owning 32 of the 128 tile columns
+constexpr int BWD_COMPUTE_WARPS = 16;
+constexpr int BWD_GROUP_WARPS = 8;
+constexpr int HALF_BYTES = 64 * HD * 2;    // 8 KB: 64 key rows of a K / V tile
 
 struct AttnBwdParams {
     const float* mask; const float* lse; const float* delta;
-    float* dq_acc;         // [B, A, S, 64] fp32 scratch: dQ accumulated over the kv tiles (unused when S == 128)
     float* dbias;          // [3H] fp32 or null: += column sums of dqkv
     bf16* dqkv;            // [T, 3H]
     int B, S, A, H;
@@ -330,7 +343,8 @@ struct AttnBwdParams {
 };
 
 __host__ __device__ inline int bwd_smem_bytes(int S) {
-    return 1024 + 2 * TILE_BYTES /*K,V*/ + 4 * TILE_BYTES /*Q,dO x2*/ + 2 * PT_BYTES /*P,dS*/ + S * 4 + 256;
+    const int n = S / TQ;
+    return 2 * TILE_BYTES /*K,V*/ + 2 * n * TILE_BYTES /*Q,dO of every query tile*/ + 2 * PT_BYTES /*P,dS*/ + S * 4 + 256;
 }
 
 // delta[b,h,s] = sum_d dO[t, h*64+d] * O[t, h*64+d]
@@ -357,52 +371,47 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ dctx, const bf16* __r
     delta[((long long)b * A + h) * S + s] = acc;
 }
 
-// TMEM -> registers: this warp's 32 lanes x 16 consecutive fp32 columns
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr) : "memory");
-}
-
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do, const AttnBwdParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t smem[];
     const int S = p.S, n = S / TQ;
     uint8_t* sK = smem;
     uint8_t* sV = sK + TILE_BYTES;
-    uint8_t* sQ = sV + TILE_BYTES;               // [2]
-    uint8_t* sdO = sQ + 2 * TILE_BYTES;          // [2]
-    uint8_t* sP = sdO + 2 * TILE_BYTES;
+    uint8_t* sQ = sV + TILE_BYTES;               // [n]
+    uint8_t* sdO = sQ + n * TILE_BYTES;          // [n]
+    uint8_t* sP = sdO + n * TILE_BYTES;
     uint8_t* sdS = sP + PT_BYTES;
     float* sMask = reinterpret_cast<float*>(sdS + PT_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + S);
-    uint64_t* qdo_full = bars;        // [2]
-    uint64_t* qdo_empty = bars + 2;   // [2]
-    uint64_t* kv_full = bars + 4;
-    uint64_t* kv_empty = bars + 5;
-    uint64_t* s_full = bars + 6;
-    uint64_t* p_full = bars + 7;      // count 256
-    uint64_t* dp_full = bars + 8;
-    uint64_t* ds_full = bars + 9;     // count 256
-    uint64_t* pair_done = bars + 10;
-    uint64_t* dkv_full = bars + 11;
-    uint64_t* dkv_read = bars + 12;   // one arrival per compute warp
-    uint64_t* dv_done = bars + 13;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+    uint64_t* kv_full = bars;         // 1
+    uint64_t* kv_empty = bars + 1;    // 1
+    uint64_t* q_full = bars + 2;      // [4]  Q_i and dO_i landed (once per head)
+    uint64_t* s_full = bars + 6;      // [2]  S half g in TMEM            (per pair)
+    uint64_t* dp_full = bars + 8;     // [2]  dP half g in TMEM           (per pair)
+    uint64_t* s_free = bars + 10;     // [2]  group g has S half g in registers   (8 warp arrivals per pair)
+    uint64_t* dp_free = bars + 12;    // [2]
+    uint64_t* p_full = bars + 14;     // P~ tile complete in smem         (16 warp arrivals per pair)
+    uint64_t* ds_full = bars + 15;    // dS tile complete in smem         (16)
+    uint64_t* dv_done = bars + 16;    // dV(t) retired: sP may be rewritten
+    uint64_t* pair_done = bars + 17;  // dK(t), dQ(t) retired: sdS may be rewritten
+    uint64_t* dkv_full = bars + 18;   // kv tile finished: dK, dV (and at the end dQ) complete
+    uint64_t* dkv_read = bars + 19;   // accumulators drained (16)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = blockIdx.x, b = blockIdx.y;
 
     if (threadIdx.x == 0) {
+        if ((smem_u32(smem) & 1023u) != 0) __trap();          // SWIZZLE_128B tiles need a 1024-byte aligned base
         tma_prefetch_desc(&tmap_qkv); tma_prefetch_desc(&tmap_do);
-        for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
-        mbar_init(kv_full, 1); mbar_init(kv_empty, 1); mbar_init(s_full, 1); mbar_init(p_full, BWD_COMPUTE_THREADS / 32);
-        mbar_init(dp_full, 1); mbar_init(ds_full, BWD_COMPUTE_THREADS / 32); mbar_init(pair_done, 1); mbar_init(dkv_full, 1);
-        mbar_init(dkv_read, BWD_COMPUTE_THREADS / 32); mbar_init(dv_done, 1);
+        mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&q_full[i], 1);
+        for (int g = 0; g < 2; ++g) {
+            mbar_init(&s_full[g], 1); mbar_init(&dp_full[g], 1);
+            mbar_init(&s_free[g], BWD_GROUP_WARPS); mbar_init(&dp_free[g], BWD_GROUP_WARPS);
+        }
+        mbar_init(p_full, BWD_COMPUTE_WARPS); mbar_init(ds_full, BWD_COMPUTE_WARPS);
+        mbar_init(dv_done, 1); mbar_init(pair_done, 1); mbar_init(dkv_full, 1); mbar_init(dkv_read, BWD_COMPUTE_WARPS);
         fence_barrier_init();
     }
     if (warp == 0) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
@@ -410,176 +419,140 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    // S | dP | dV | dK | dQ(current pair only): S and dP no longer share columns, so S(t+1) is issued while dS(t) is being computed and
-    // dP(t+1) while P(t+1) is -- every MMA hides behind a compute phase.  dQ of the pair is drained to an fp32 global scratch block by the
-    // compute warps (same thread, same elements, fixed j order: deterministic) and converted to bf16 with the last kv tile.
-    const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 128, tmem_dV = tmem_base + 256, tmem_dK = tmem_base + 320, tmem_dQ = tmem_base + 384;
+    const uint32_t tmem_dQ = tmem_base, tmem_dK = tmem_base + 256, tmem_dV = tmem_base + 320, tmem_S = tmem_base + 384, tmem_dP = tmem_base + 448;
 
     if (warp == 0) {
+        // ===================== TMA producer =====================
         if (lane == 0) {
-            for (int j = 0; j < n; ++j) {
-                mbar_wait(kv_empty, (j & 1) ^ 1);
+            mbar_expect_tx(kv_full, 2 * TILE_BYTES);
+            tma_load_3d(sK, &tmap_qkv, kv_full, p.H + h * HD, 0, b);
+            tma_load_3d(sV, &tmap_qkv, kv_full, 2 * p.H + h * HD, 0, b);
+            for (int i = 0; i < n; ++i) {
+                mbar_expect_tx(&q_full[i], 2 * TILE_BYTES);
+                tma_load_3d(sQ + i * TILE_BYTES, &tmap_qkv, &q_full[i], h * HD, i * TQ, b);
+                tma_load_3d(sdO + i * TILE_BYTES, &tmap_do, &q_full[i], h * HD, i * TQ, b);
+            }
+            for (int j = 1; j < n; ++j) {
+                mbar_wait(kv_empty, (j - 1) & 1);            // every MMA that reads K_{j-1} / V_{j-1} has retired
                 mbar_expect_tx(kv_full, 2 * TILE_BYTES);
                 tma_load_3d(sK, &tmap_qkv, kv_full, p.H + h * HD, j * TQ, b);
                 tma_load_3d(sV, &tmap_qkv, kv_full, 2 * p.H + h * HD, j * TQ, b);
-                for (int i = 0; i < n; ++i) {
-                    const int t = j * n + i, st = t & 1;
-                    mbar_wait(&qdo_empty[st], ((t >> 1) & 1) ^ 1);
-                    mbar_expect_tx(&qdo_full[st], 2 * TILE_BYTES);
-                    tma_load_3d(sQ + st * TILE_BYTES, &tmap_qkv, &qdo_full[st], h * HD, i * TQ, b);
-                    tma_load_3d(sdO + st * TILE_BYTES, &tmap_do, &qdo_full[st], h * HD, i * TQ, b);
-                }
             }
         }
     } else if (warp == 1) {
+        // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t id_kk = make_idesc_bf16(TQ, TQ, false, false);     // S, dP
+            constexpr uint32_t id_h = make_idesc_bf16(TQ, 64, false, false);      // S half, dP half: [128 q] x [64 keys], K = d
             constexpr uint32_t id_mm = make_idesc_bf16(TQ, HD, true, true);       // dV, dK
             constexpr uint32_t id_km = make_idesc_bf16(TQ, HD, false, true);      // dQ
-            const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP), adS = smem_u32(sdS);
-            // Issue order per pair t = j*n + i (S and dP own separate TMEM columns):
-            //   p_full(t):  S(t+1) -> dV(t)            (S columns are free once P(t) was computed from them)
-            //   ds_full(t): dP(t+1) -> dK(t), dQ(t)    (dP columns are free once dS(t) was computed; dQ(t-1) was drained before ds_full(t))
-            // so S(t+1) executes while the compute warps are in the dS(t) phase and dP(t+1) while they are in the P(t+1) phase.
-            auto issue_s = [&](int t_) {
-                const uint32_t aQ_ = smem_u32(sQ) + (t_ & 1) * TILE_BYTES;
-                mbar_wait(&qdo_full[t_ & 1], (t_ >> 1) & 1);
-                tc_fence_after();
+            const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ0 = smem_u32(sQ), adO0 = smem_u32(sdO), aP = smem_u32(sP), adS = smem_u32(sdS);
+            auto issue_s = [&](int i_, int g_) {                // S(t, g) = Q_i K_{j, half g}^T
+                const uint32_t aQ = aQ0 + i_ * TILE_BYTES, aKh = aK + g_ * HALF_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
-                    umma_bf16_ss(tmem_S, make_smem_desc_sw128(aQ_ + kk * 32, 0, 1024), make_smem_desc_sw128(aK + kk * 32, 0, 1024),
-                                 id_kk, kk > 0 ? 1u : 0u);
-                umma_commit(s_full);
+                    umma_bf16_ss(tmem_S, make_smem_desc_sw128(aQ + kk * 32, 0, 1024), make_smem_desc_sw128(aKh + kk * 32, 0, 1024), id_h, kk > 0 ? 1u : 0u);
+                umma_commit(&s_full[g_]);
             };
-            auto issue_dp = [&](int t_) {                       // qdo_full[t_ & 1] was already observed by issue_s(t_)
-                const uint32_t adO_ = smem_u32(sdO) + (t_ & 1) * TILE_BYTES;
+            auto issue_dp = [&](int i_, int g_) {               // dP(t, g) = dO_i V_{j, half g}^T
+                const uint32_t adO = adO0 + i_ * TILE_BYTES, aVh = aV + g_ * HALF_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
-                    umma_bf16_ss(tmem_dP, make_smem_desc_sw128(adO_ + kk * 32, 0, 1024), make_smem_desc_sw128(aV + kk * 32, 0, 1024),
-                                 id_kk, kk > 0 ? 1u : 0u);
-                umma_commit(dp_full);
+                    umma_bf16_ss(tmem_dP, make_smem_desc_sw128(adO + kk * 32, 0, 1024), make_smem_desc_sw128(aVh + kk * 32, 0, 1024), id_h, kk > 0 ? 1u : 0u);
+                umma_commit(&dp_full[g_]);
             };
+            auto issue_dv = [&](int i_) {                       // dV_j += P~^T dO_i
+                const uint32_t adO = adO0 + i_ * TILE_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
+                    umma_bf16_ss(tmem_dV, make_smem_desc_sw128(aP + kk * 2048, TILE_BYTES, 1024),
+                                 make_smem_desc_sw128(adO + kk * 2048, TILE_BYTES, 1024), id_mm, (i_ > 0 || kk > 0) ? 1u : 0u);
+                umma_commit(dv_done);
+            };
+            auto issue_dkdq = [&](int i_, int j_) {             // dK_j += dS^T Q_i ; dQ_i += dS K_j
+                const uint32_t aQ = aQ0 + i_ * TILE_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
+                    umma_bf16_ss(tmem_dK, make_smem_desc_sw128(adS + kk * 2048, TILE_BYTES, 1024),
+                                 make_smem_desc_sw128(aQ + kk * 2048, TILE_BYTES, 1024), id_mm, (i_ > 0 || kk > 0) ? 1u : 0u);
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk)
+                    umma_bf16_ss(tmem_dQ + i_ * HD, make_smem_desc_sw128(adS + (kk >> 2) * TILE_BYTES + (kk & 3) * 32, 0, 1024),
+                                 make_smem_desc_sw128(aK + kk * 2048, TILE_BYTES, 1024), id_km, (j_ > 0 || kk > 0) ? 1u : 0u);
+                umma_commit(pair_done);
+            };
+            auto wait = [&](uint64_t* bar, int phase) { mbar_wait(bar, (uint32_t)phase & 1u); tc_fence_after(); };
             for (int j = 0; j < n; ++j) {
-                mbar_wait(kv_full, j & 1);
-                if (j >= 1) mbar_wait(dkv_read, (j - 1) & 1);       // dV/dK accumulators (and the last dQ of the previous tile) drained
-                tc_fence_after();
-                issue_s(j * n);                                      // first pair of this kv tile: both inputs of the compute warps up front
-                issue_dp(j * n);
+                wait(kv_full, j);
+                if (j >= 1) wait(dkv_read, j - 1);              // dK / dV accumulators of the previous kv tile drained
                 for (int i = 0; i < n; ++i) {
-                    const int t = j * n + i, st = t & 1;
-                    const uint32_t aQ = smem_u32(sQ) + st * TILE_BYTES, adO = smem_u32(sdO) + st * TILE_BYTES;
-                    mbar_wait(p_full, t & 1);                        // P~(t) in smem, S(t) consumed
-                    tc_fence_after();
-                    if (i + 1 < n) issue_s(t + 1);
-#pragma unroll
-                    for (int kk = 0; kk < 8; ++kk)                  // dV_j += P~^T dO_i
-                        umma_bf16_ss(tmem_dV, make_smem_desc_sw128(aP + kk * 2048, TILE_BYTES, 1024),
-                                     make_smem_desc_sw128(adO + kk * 2048, TILE_BYTES, 1024), id_mm, (i > 0 || kk > 0) ? 1u : 0u);
-                    umma_commit(dv_done);                            // sP may be overwritten
-                    mbar_wait(ds_full, t & 1);                       // dS(t) in smem, dP(t) consumed, dQ(t-1) drained
-                    tc_fence_after();
-                    if (i + 1 < n) issue_dp(t + 1);
-#pragma unroll
-                    for (int kk = 0; kk < 8; ++kk)                  // dK_j += dS^T Q_i
-                        umma_bf16_ss(tmem_dK, make_smem_desc_sw128(adS + kk * 2048, TILE_BYTES, 1024),
-                                     make_smem_desc_sw128(aQ + kk * 2048, TILE_BYTES, 1024), id_mm, (i > 0 || kk > 0) ? 1u : 0u);
-#pragma unroll
-                    for (int kk = 0; kk < 8; ++kk)                  // dQ_ij = dS K_j (this pair only; accumulated over j in global memory)
-                        umma_bf16_ss(tmem_dQ, make_smem_desc_sw128(adS + (kk >> 2) * TILE_BYTES + (kk & 3) * 32, 0, 1024),
-                                     make_smem_desc_sw128(aK + kk * 2048, TILE_BYTES, 1024), id_km, kk > 0 ? 1u : 0u);
-                    umma_commit(&qdo_empty[st]);
-                    umma_commit(pair_done);
+                    const int t = j * n + i;
+                    if (j == 0) wait(&q_full[i], 0);
+                    if (t >= 1) wait(&s_free[1], t - 1);        // group 1 has S(t-1, 1) in registers: the S columns are free
+                    issue_s(i, 0);
+                    if (t >= 1) wait(&dp_free[1], t - 1);
+                    issue_dp(i, 0);
+                    wait(&s_free[0], t);
+                    issue_s(i, 1);
+                    if (i >= 1) { wait(p_full, t - 1); issue_dv(i - 1); }
+                    wait(&dp_free[0], t);
+                    issue_dp(i, 1);
+                    if (i >= 1) { wait(ds_full, t - 1); issue_dkdq(i - 1, j); }
                 }
+                const int tl = j * n + n - 1;                   // the trailing pair of this kv tile
+                wait(p_full, tl); issue_dv(n - 1);
+                wait(ds_full, tl); issue_dkdq(n - 1, j);
                 umma_commit(kv_empty);
                 umma_commit(dkv_full);
             }
         }
     } else {
         // ===================== compute warps =====================
-        const int q4 = warp & 3, qc = (warp - 2) >> 2;          // qc: which 32-column quarter of the tile
+        const int q4 = warp & 3;                                // TMEM lane quarter (hardware rule: warp id % 4)
+        const int wi = (warp - 2) >> 2;                         // 0..3
+        const int g = wi >> 1, c = wi & 1;                      // key half of the pair this warp's group owns; 32-column half of that
         const int r = q4 * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
         const int ct = threadIdx.x - 64;
-        for (int i = ct; i < S; i += BWD_COMPUTE_THREADS) sMask[i] = p.mask ? p.mask[(long long)b * S + i] * LOG2E : 0.f;
-        named_bar_sync(1, BWD_COMPUTE_THREADS);
+        for (int i = ct; i < S; i += BWD_COMPUTE_WARPS * 32) sMask[i] = p.mask ? p.mask[(long long)b * S + i] * LOG2E : 0.f;
+        named_bar_sync(1, BWD_COMPUTE_WARPS * 32);
         const long long bh = (long long)b * p.A + h;
         const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS);
         const unsigned long long seed = effective_seed(p.seed, p.seed_dev);
-        // dQ of pair (j, i): 128 x 64 fp32 in TMEM; this thread owns row r, columns [qc*16, +16) -- the same thread touches the same 16
-        // addresses for every j, in program order, so the accumulation order is fixed.  j == 0 stores, 0 < j < n-1 adds (red), the last
-        // kv tile reads the running sum back, adds its own part and writes bf16 (+ the query-bias column sums).
-        auto drain_dq = [&](int j_, int i_) {
-            uint32_t w[16];
-            tmem_ld16(tmem_dQ + lane_addr + qc * 16, w);
-            tmem_ld_wait();
-            float* acc = p.dq_acc + ((bh * S + i_ * TQ + r) * HD + qc * 16);
-            if (j_ + 1 < n) {
-                if (j_ == 0) {
-#pragma unroll
-                    for (int k = 0; k < 16; k += 4)
-                        *reinterpret_cast<float4*>(acc + k) = make_float4(__uint_as_float(w[k]), __uint_as_float(w[k + 1]), __uint_as_float(w[k + 2]), __uint_as_float(w[k + 3]));
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 16; k += 4)
-                        red_add_v4_f32(acc + k, __uint_as_float(w[k]), __uint_as_float(w[k + 1]), __uint_as_float(w[k + 2]), __uint_as_float(w[k + 3]));
-                }
-                return;
-            }
-            float f[32];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(w[k]);
-            if (n > 1) {
-#pragma unroll
-                for (int k = 0; k < 16; k += 4) {
-                    const float4 prev = __ldcg(reinterpret_cast<const float4*>(acc + k));
-                    f[k] += prev.x; f[k + 1] += prev.y; f[k + 2] += prev.z; f[k + 3] += prev.w;
-                }
-            }
-            const long long tok_q = (long long)b * p.tok_stride_b + (long long)(i_ * TQ + r) * p.tok_stride_s;
-            bf16* o = p.dqkv + tok_q * (3LL * p.H) + h * HD + qc * 16;
-#pragma unroll
-            for (int k = 0; k < 16; k += 8)
-                st_global_v4(o + k, pack_bf16(f[k], f[k + 1]), pack_bf16(f[k + 2], f[k + 3]), pack_bf16(f[k + 4], f[k + 5]), pack_bf16(f[k + 6], f[k + 7]));
-            if (p.dbias != nullptr) {                            // query bias gradient: column sums of the stored bf16 values
-#pragma unroll
-                for (int k = 0; k < 16; ++k) f[k] = __bfloat162float(__float2bfloat16_rn(f[k]));
-#pragma unroll
-                for (int k = 16; k < 32; ++k) f[k] = 0.f;
-                const float cs = warp_column_sums32(f, lane);
-                if (lane < 16) atomicAdd(p.dbias + h * HD + qc * 16 + lane, cs);
-            }
-        };
+        const int kc = g * 64 + c * 32;                         // first key column (within the 128-key tile) of this thread
+        const float c1 = p.drop_scale * p.scale;
         for (int j = 0; j < n; ++j) {
             // my 32 key columns of this kv tile: additive mask (already x log2e) from shared memory, skipped entirely when it is all
-            // zero (warp-uniform; unpadded batches).  Explicit ld.shared: the generic loads the compiler emitted for sMask[] went
-            // through the global/local queue (ncu: 4 % of the kernel's samples on `lg` throttle at those eight loads).
-            const uint32_t mk_addr = smem_u32(sMask + j * TQ + qc * 32);
-            const bool masked = __any_sync(0xffffffffu, sMask[j * TQ + qc * 32 + lane] != 0.f);
+            // zero (warp-uniform; unpadded batches)
+            const uint32_t mk_addr = smem_u32(sMask + j * TQ + kc);
+            const bool masked = __any_sync(0xffffffffu, sMask[j * TQ + kc + lane] != 0.f);
             for (int i = 0; i < n; ++i) {
                 const int t = j * n + i;
-                const float lse2 = p.lse[bh * S + i * TQ + r] * LOG2E;
-                const float dl = p.delta[bh * S + i * TQ + r];
-                const unsigned long long drop_row = (unsigned long long)(bh * S + (i * TQ + r)) * (unsigned long long)S + j * TQ + qc * 32;
+                const uint32_t ph = (uint32_t)t & 1u;
+                const float neg_lse2 = -p.lse[bh * S + i * TQ + r] * LOG2E;
+                const float nd = -p.delta[bh * S + i * TQ + r] * p.scale;
+                const unsigned long long drop_row = (unsigned long long)(bh * S + (i * TQ + r)) * (unsigned long long)S + j * TQ + kc;
                 uint32_t pk[16];                 // undropped P, packed bf16x2 (32 values)
                 uint32_t km[16];                 // keep-masks of my 32 columns (bf16x2 AND-masks)
-                mbar_wait(s_full, t & 1);
-                tc_fence_after();
-                if (t >= 1) { mbar_wait(dv_done, (t - 1) & 1); tc_fence_after(); }     // dV(t-1) retired: sP may be overwritten
                 uint32_t v[32];
+                // ---- P = exp2(S * scale + mask - lse)
+                mbar_wait(&s_full[g], ph);
+                tc_fence_after();
+                tmem_ld32(tmem_S + lane_addr + c * 32, v);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_free[g]);         // the S columns may be overwritten (other half / next pair)
                 {
-                    tmem_ld32(tmem_S + lane_addr + qc * 32, v);
-                    tmem_ld_wait();
                     float e[32];
-                    const float neg_lse2 = -lse2;
                     if (masked) {
 #pragma unroll
-                        for (int g = 0; g < 8; ++g) {
+                        for (int q = 0; q < 8; ++q) {
                             float m0, m1, m2, m3;
-                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(m0), "=f"(m1), "=f"(m2), "=f"(m3) : "r"(mk_addr + g * 16));
-                            e[4 * g + 0] = ex2(fmaf(__uint_as_float(v[4 * g + 0]), p.scale_log2, m0) + neg_lse2);
-                            e[4 * g + 1] = ex2(fmaf(__uint_as_float(v[4 * g + 1]), p.scale_log2, m1) + neg_lse2);
-                            e[4 * g + 2] = ex2(fmaf(__uint_as_float(v[4 * g + 2]), p.scale_log2, m2) + neg_lse2);
-                            e[4 * g + 3] = ex2(fmaf(__uint_as_float(v[4 * g + 3]), p.scale_log2, m3) + neg_lse2);
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(m0), "=f"(m1), "=f"(m2), "=f"(m3) : "r"(mk_addr + q * 16));
+                            e[4 * q + 0] = ex2(fmaf(__uint_as_float(v[4 * q + 0]), p.scale_log2, m0) + neg_lse2);
+                            e[4 * q + 1] = ex2(fmaf(__uint_as_float(v[4 * q + 1]), p.scale_log2, m1) + neg_lse2);
+                            e[4 * q + 2] = ex2(fmaf(__uint_as_float(v[4 * q + 2]), p.scale_log2, m2) + neg_lse2);
+                            e[4 * q + 3] = ex2(fmaf(__uint_as_float(v[4 * q + 3]), p.scale_log2, m3) + neg_lse2);
                         }
                     } else {
 #pragma unroll
@@ -591,70 +564,62 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
                     }
 #pragma unroll
                     for (int k = 0; k < 16; ++k) pk[k] = pack_bf16(e[2 * k], e[2 * k + 1]);
-                    // P~ = keep-mask AND P: the 1/(1-p) factor is folded into the dV drain and into the dS constants below
-                    if (p.drop_on != 0u) {
-                        attn_dropout_masks16(seed, p.drop_stream, drop_row >> 5, p.drop_k2, km);
-#pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            st_shared_v4(aP + pt_offset(r, qc * 32 + g * 8), pk[g * 4] & km[g * 4], pk[g * 4 + 1] & km[g * 4 + 1],
-                                         pk[g * 4 + 2] & km[g * 4 + 2], pk[g * 4 + 3] & km[g * 4 + 3]);
-                    } else {
-#pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            st_shared_v4(aP + pt_offset(r, qc * 32 + g * 8), pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
-                    }
                 }
-                tc_fence_before();
+                if (p.drop_on != 0u) attn_dropout_masks16(seed, p.drop_stream, drop_row >> 5, p.drop_k2, km);
+                if (t >= 1) { mbar_wait(dv_done, ph ^ 1u); tc_fence_after(); }          // dV(t-1) retired: sP may be overwritten
+                // P~ = keep-mask AND P: the 1/(1-p) factor is folded into the dV drain and into the dS constants below
+                if (p.drop_on != 0u) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        st_shared_v4(aP + pt_offset(r, kc + q * 8), pk[q * 4] & km[q * 4], pk[q * 4 + 1] & km[q * 4 + 1],
+                                     pk[q * 4 + 2] & km[q * 4 + 2], pk[q * 4 + 3] & km[q * 4 + 3]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        st_shared_v4(aP + pt_offset(r, kc + q * 8), pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+                }
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(p_full);
-                // ---- dK/dQ(t-1) retired: sdS may be overwritten, and dQ(t-1) (previous query tile, same kv tile) is ready to be drained.
-                //      This sits between the two phases so that it overlaps with dP(t) / S(t+1) on the tensor core.
-                if (t >= 1) { mbar_wait(pair_done, (t - 1) & 1); tc_fence_after(); }
-                if (i >= 1) drain_dq(j, i - 1);
                 // ---- dS = [ (mask & P) * dP / (1-p) - P * delta ] * scale
-                mbar_wait(dp_full, t & 1);
+                mbar_wait(&dp_full[g], ph);
                 tc_fence_after();
-                {
-                    tmem_ld32(tmem_dP + lane_addr + qc * 32, v);
-                    tmem_ld_wait();
-                    const float c1 = p.drop_scale * p.scale, nd = -dl * p.scale;
-                    uint32_t ds[16];
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) {
-                        const uint32_t pm = (p.drop_on != 0u) ? (pk[k] & km[k]) : pk[k];
-                        float t0, t1, u0, u1, d0, d1;
-                        fmul2(t0, t1, __uint_as_float(pm << 16), __uint_as_float(pm & 0xFFFF0000u), __uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]));
-                        fmul2(u0, u1, __uint_as_float(pk[k] << 16), __uint_as_float(pk[k] & 0xFFFF0000u), nd, nd);
-                        ffma2(d0, d1, t0, t1, c1, c1, u0, u1);
-                        ds[k] = pack_bf16(d0, d1);
-                    }
-#pragma unroll
-                    for (int g = 0; g < 4; ++g)
-                        st_shared_v4(adS + pt_offset(r, qc * 32 + g * 8), ds[g * 4], ds[g * 4 + 1], ds[g * 4 + 2], ds[g * 4 + 3]);
-                }
+                tmem_ld32(tmem_dP + lane_addr + c * 32, v);
+                tmem_ld_wait();
                 tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&dp_free[g]);
+                uint32_t ds[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const uint32_t pm = (p.drop_on != 0u) ? (pk[k] & km[k]) : pk[k];
+                    float t0, t1, u0, u1, d0, d1;
+                    fmul2(t0, t1, __uint_as_float(pm << 16), __uint_as_float(pm & 0xFFFF0000u), __uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]));
+                    fmul2(u0, u1, __uint_as_float(pk[k] << 16), __uint_as_float(pk[k] & 0xFFFF0000u), nd, nd);
+                    ffma2(d0, d1, t0, t1, c1, c1, u0, u1);
+                    ds[k] = pack_bf16(d0, d1);
+                }
+                if (t >= 1) { mbar_wait(pair_done, ph ^ 1u); tc_fence_after(); }        // dK / dQ(t-1) retired: sdS may be overwritten
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    st_shared_v4(adS + pt_offset(r, kc + q * 8), ds[q * 4], ds[q * 4 + 1], ds[q * 4 + 2], ds[q * 4 + 3]);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(ds_full);
             }
-            // ---- dV_j, dK_j complete (and with them the last pair's dQ): drain to global
+            // ---- dV_j, dK_j complete: group 0 drains dK, group 1 drains dV (32 columns per warp)
             mbar_wait(dkv_full, j & 1);
             tc_fence_after();
-            drain_dq(j, n - 1);
-            const long long tok = (long long)b * p.tok_stride_b + (long long)(j * TQ + r) * p.tok_stride_s;
-            uint32_t v[32];
-            if (qc < 2) {                                        // 64-wide accumulators: two of the four column-warps drain them
-            const int hf = qc;
-#pragma unroll
-            for (int which = 0; which < 2; ++which) {           // 0: dK (col block 1), 1: dV (col block 2)
-                tmem_ld32((which == 0 ? tmem_dK : tmem_dV) + lane_addr + hf * 32, v);
+            {
+                const long long tok = (long long)b * p.tok_stride_b + (long long)(j * TQ + r) * p.tok_stride_s;
+                uint32_t v[32];
+                tmem_ld32((g == 0 ? tmem_dK : tmem_dV) + lane_addr + c * 32, v);
                 tmem_ld_wait();
-                if (which == 1 && p.drop_on != 0u) {             // dV accumulated keep-mask AND P: apply the 1/(1-p) factor here
+                if (g == 1 && p.drop_on != 0u) {                 // dV accumulated keep-mask AND P: apply the 1/(1-p) factor here
 #pragma unroll
                     for (int k = 0; k < 32; ++k) v[k] = __float_as_uint(__uint_as_float(v[k]) * p.drop_scale);
                 }
-                bf16* o = p.dqkv + tok * (3LL * p.H) + (which + 1) * p.H + h * HD + hf * 32;
+                bf16* o = p.dqkv + tok * (3LL * p.H) + (g + 1) * p.H + h * HD + c * 32;
 #pragma unroll
                 for (int k = 0; k < 32; k += 8)
                     st_global_v4(o + k, pack_bf16(__uint_as_float(v[k]), __uint_as_float(v[k + 1])), pack_bf16(__uint_as_float(v[k + 2]), __uint_as_float(v[k + 3])),
@@ -664,13 +629,32 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
 #pragma unroll
                     for (int k = 0; k < 32; ++k) f[k] = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[k])));
                     const float cs = warp_column_sums32(f, lane);
-                    atomicAdd(p.dbias + (which + 1) * p.H + h * HD + hf * 32 + lane, cs);
+                    atomicAdd(p.dbias + (g + 1) * p.H + h * HD + c * 32 + lane, cs);
                 }
-            }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(dkv_read);
+        }
+        // ---- all pairs done (dkv_full of the last kv tile implies every MMA retired): drain dQ, two 32-column chunks per warp
+        for (int ch = wi; ch < 2 * n; ch += 4) {
+            const int i = ch >> 1, hf = ch & 1;
+            uint32_t v[32];
+            tmem_ld32(tmem_dQ + i * HD + lane_addr + hf * 32, v);
+            tmem_ld_wait();
+            const long long tok = (long long)b * p.tok_stride_b + (long long)(i * TQ + r) * p.tok_stride_s;
+            bf16* o = p.dqkv + tok * (3LL * p.H) + h * HD + hf * 32;
+#pragma unroll
+            for (int k = 0; k < 32; k += 8)
+                st_global_v4(o + k, pack_bf16(__uint_as_float(v[k]), __uint_as_float(v[k + 1])), pack_bf16(__uint_as_float(v[k + 2]), __uint_as_float(v[k + 3])),
+                             pack_bf16(__uint_as_float(v[k + 4]), __uint_as_float(v[k + 5])), pack_bf16(__uint_as_float(v[k + 6]), __uint_as_float(v[k + 7])));
+            if (p.dbias != nullptr) {                            // query bias gradient
+                float f[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) f[k] = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[k])));
+                const float cs = warp_column_sums32(f, lane);
+                atomicAdd(p.dbias + h * HD + hf * 32 + lane, cs);
+            }
         }
     }
     tc_fence_before();
@@ -762,7 +746,7 @@ extern "C" int dle_attn_bwd(const void* qkv, const float* mask, const void* ctx,
     attn_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(dctx), reinterpret_cast<const bf16*>(ctx), delta_ws, B, S, A, seq_first);
     DLE_LAUNCH_CHECK();
     AttnBwdParams p;
-    p.mask = mask; p.lse = lse; p.delta = delta_ws; p.dq_acc = delta_ws + (long long)B * A * S; p.dbias = dbias_qkv; p.dqkv = reinterpret_cast<bf16*>(dqkv);
+    p.mask = mask; p.lse = lse; p.delta = delta_ws; p.dbias = dbias_qkv; p.dqkv = reinterpret_cast<bf16*>(dqkv);
     p.B = B; p.S = S; p.A = A; p.H = H; p.tok_stride_s = seq_first ? B : 1; p.tok_stride_b = seq_first ? 1 : S; p.scale = 0.125f; p.scale_log2 = 0.125f * LOG2E;
     attn_drop_params(dropout_p, &p.drop_k2, &p.drop_on, &p.drop_scale);
     p.drop_stream = dropout_stream; p.seed = seed; p.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);

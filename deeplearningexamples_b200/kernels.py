@@ -104,8 +104,7 @@ def attn_bwd(qkv, mask, ctx, dctx, lse, B, S, A, dropout_p=0.0, seed=0, dropout_
     """dbias: optional zeroed fp32 [3H] receiving the column sums of dqkv (q/k/v bias gradients)."""
     lib = L.load()
     dqkv = torch.empty_like(qkv)
-    # row dots [B,A,S] followed by the fp32 dQ accumulator [B,A,S,64] the kernel sums over the key tiles (include/dle_b200.h)
-    delta = torch.empty(B * A * S * (65 if S > 128 else 1), device=qkv.device, dtype=torch.float32)
+    delta = torch.empty((B, A, S), device=qkv.device, dtype=torch.float32)
     L.launch_count["n"] += 2; L.check(lib.dle_attn_bwd(_ptr(qkv), _ptr(mask), _ptr(ctx), _ptr(_req(dctx, bf16, "dctx")), _ptr(lse), _ptr(dqkv),
                              _ptr(delta), _ptr(dbias), B, S, A, 1 if seq_first else 0, dropout_p, seed, _ptr(seed_dev), dropout_stream, _stream()), "dle_attn_bwd")
     return dqkv

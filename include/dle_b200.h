@@ -101,8 +101,8 @@ int dle_gemm_bf16(const dle_gemm_args* host_args, void* stream);
  * ------------------------------------------------------------------------------------------ */
 int dle_attn_fwd(const void* qkv, const float* mask, void* ctx, float* lse, int32_t B, int32_t S, int32_t A,
                  int32_t seq_first, float dropout_p, uint64_t seed, const uint64_t* seed_dev, uint32_t dropout_stream, void* stream);
-/* delta_ws: fp32 workspace of B*A*S*65 floats ([B,A,S] row dots followed by the [B,A,S,64] dQ accumulator; B*A*S suffices when S == 128);
- * dqkv: bf16 [B*S, 3*A*64], fully overwritten;
+/* delta_ws: fp32 workspace [B, A, S] (row dots of dO and O); dqkv: bf16 [B*S, 3*A*64], fully overwritten (dQ, dK and dV are
+ * accumulated in tensor memory: no atomics, bitwise reproducible);
  * dbias_qkv: fp32 [3*A*64] or NULL: += column sums of dqkv (the q/k/v bias gradients), must be zeroed by the caller */
 int dle_attn_bwd(const void* qkv, const float* mask, const void* ctx, const void* dctx, const float* lse,
                  void* dqkv, float* delta_ws, float* dbias_qkv, int32_t B, int32_t S, int32_t A, int32_t seq_first, float dropout_p,
