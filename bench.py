@@ -260,6 +260,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        if not (args.no_cuda_graphs or args.dynamic_mlm_gather):
+            # whole-step capture under DDP: NCCL's async error handling must be off, as the reference sets it (run_pretraining.py:334-335)
+            os.environ.setdefault("NCCL_ASYNC_ERROR_HANDLING", "0")
+            os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
         dist.init_process_group(backend="nccl", init_method="env://", device_id=device)
     L.load()
     cfg, S, B, P = workload(args)
@@ -341,10 +345,15 @@ def run_ours(args):
             stage[k].copy_(dev[0][k])
         n_eager = max(n_warm, 11 if world > 1 else 3)
         n_before = L.launch_count["n"]
-        graph["g"] = T.capture_step_graph(one_step, warmup_iters=n_eager)
-        launches_per_step = (L.launch_count["n"] - n_before) // (n_eager + 1)
-        torch.cuda.synchronize()
-        log(f"captured the step into a CUDA graph after {n_eager} eager warm-up steps ({launches_per_step} kernels of libdle_b200.so per step)")
+        try:
+            graph["g"] = T.capture_step_graph(one_step, warmup_iters=n_eager)
+            launches_per_step = (L.launch_count["n"] - n_before) // (n_eager + 1)
+            torch.cuda.synchronize()
+            log(f"captured the step into a CUDA graph after {n_eager} eager warm-up steps ({launches_per_step} kernels of libdle_b200.so per step)")
+        except Exception as e:                      # report, then measure the eager path rather than nothing
+            graph["g"], launches_per_step, use_graphs = None, None, False
+            log(f"CUDA-graph capture failed ({type(e).__name__}: {str(e)[:200]}); continuing with eager launches")
+            torch.cuda.synchronize()
         n_warm = n_eager
         for i in range(2):
             step_resident(i)
@@ -431,6 +440,7 @@ def run_ours(args):
                                         "achieved_tflops_per_gpu": round(value / n * flops_seq / 1e12, 1),
                                         "frac_of_sustained_peak": round(value / n * flops_seq / 1e12 / pk["tf_sustained"], 4)},
             "final_loss": round(final_loss, 4)}
+    line["config"]["cuda_graphs"] = bool(use_graphs)
     if clocks is not None:
         line["clocks"] = clocks
     if rank == 0 and n == 1 and not args.no_cpu_baseline and not squad:

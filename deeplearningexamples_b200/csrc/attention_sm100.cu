@@ -47,7 +47,7 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 //   CTA   : one (batch, head, 128-query tile); sized for TWO co-resident CTAs per SM so one CTA's softmax overlaps the other's MMAs
 //   smem  : Q 16 KB + K ring 2x16 KB + V ring 2x16 KB + P 32 KB + 512 B max exchange + barriers = 112.6 KB  -> 2 CTAs in 228 KB
 //   TMEM  : S 128 cols + O 64 cols -> 256-column allocation                                             -> 2 CTAs in 512 cols
-//   warps : 0 = TMA producer (+TMEM alloc), 1 = MMA issuer, 2..9 = softmax.  TWO threads per query row: the two warps of a TMEM lane
+//   warps : 0..7 = softmax, 8 = TMA producer (+TMEM alloc), 9 = MMA issuer.  TWO threads per query row: the two warps of a TMEM lane
 //           quarter each own 64 of the 128 key columns of a chunk (v2 had one thread per row = 2 softmax warps per scheduler with both
 //           CTAs resident and was dependency-bound: ncu 44 % issue-active).  The halves agree on the chunk's row maximum through a
 //           512 B shared exchange (bf16, rounded UP so that exp2(s - m) <= 1 still holds) and a 64-thread named barrier.
@@ -56,7 +56,8 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 //   math  : packed FFMA2/FADD2 for scale-subtract and the row sums; dropout keeps arrive as bf16x2 AND-masks (common.cuh).
 // =================================================================================================
 constexpr int FWD_SOFTMAX_WARPS = 8;
-constexpr int FWD_THREADS = (2 + FWD_SOFTMAX_WARPS) * 32;      // 320
+constexpr int FWD_THREADS = (2 + FWD_SOFTMAX_WARPS) * 32;      // 320: warps 0..7 softmax, 8 TMA producer (+TMEM alloc), 9 MMA issuer (highest ids:
+constexpr int FWD_WARP_TMA = FWD_SOFTMAX_WARPS, FWD_WARP_MMA = FWD_SOFTMAX_WARPS + 1;      // the arbiter favours them over the softmax warps)
 constexpr int FWD_TMEM_COLS = 256;
 constexpr int FWD_XCHG_BYTES = 2 * TQ * 2;                     // [half][row] bf16
 constexpr int FWD_BAR_BYTES = 128;
@@ -105,56 +106,67 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdParam
         mbar_init(s_full, 1); mbar_init(p_full, FWD_SOFTMAX_WARPS); mbar_init(pv_done, 1);
         fence_barrier_init();
     }
-    if (warp == 0) { tmem_alloc(tmem_ptr, FWD_TMEM_COLS); tmem_relinquish(); }
+    if (warp == FWD_WARP_TMA) { tmem_alloc(tmem_ptr, FWD_TMEM_COLS); tmem_relinquish(); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + TQ;
 
-    if (warp == 0) {
+    // Producer and MMA warps: warp-uniform loops (all lanes wait), tcgen05 / TMA instructions under elect_one() -- see gemm_sm100.cu.
+    if (warp == FWD_WARP_TMA) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(q_full, TILE_BYTES);
             tma_load_3d(sQ, &tmap_qkv, q_full, h * HD, qt * TQ, b);
-            for (int j = 0; j < n_chunks; ++j) {
-                const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
-                mbar_wait(&k_empty[st], ph ^ 1);
+        }
+        __syncwarp();
+        for (int j = 0; j < n_chunks; ++j) {
+            const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
+            mbar_wait(&k_empty[st], ph ^ 1);
+            if (elect_one()) {
                 mbar_expect_tx(&k_full[st], TILE_BYTES);
                 tma_load_3d(sK + st * TILE_BYTES, &tmap_qkv, &k_full[st], p.H + h * HD, j * TQ, b);
-                mbar_wait(&v_empty[st], ph ^ 1);
+            }
+            __syncwarp();
+            mbar_wait(&v_empty[st], ph ^ 1);
+            if (elect_one()) {
                 mbar_expect_tx(&v_full[st], TILE_BYTES);
                 tma_load_3d(sV + st * TILE_BYTES, &tmap_qkv, &v_full[st], 2 * p.H + h * HD, j * TQ, b);
             }
+            __syncwarp();
         }
-    } else if (warp == 1) {
+    } else if (warp == FWD_WARP_MMA) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc_s = make_idesc_bf16(TQ, TQ, false, false);
-            constexpr uint32_t idesc_pv = make_idesc_bf16(TQ, HD, false, true);
-            const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
-            auto issue_s = [&](int j_) {                       // S_j = Q K_j^T
-                const int st = j_ & 1;
-                mbar_wait(&k_full[st], (j_ >> 1) & 1);
-                tc_fence_after();
+        constexpr uint32_t idesc_s = make_idesc_bf16(TQ, TQ, false, false);
+        constexpr uint32_t idesc_pv = make_idesc_bf16(TQ, HD, false, true);
+        const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
+        auto issue_s = [&](int j_) {                       // S_j = Q K_j^T
+            const int st = j_ & 1;
+            mbar_wait(&k_full[st], (j_ >> 1) & 1);
+            tc_fence_after();
+            if (elect_one()) {
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
                     umma_bf16_ss(tmem_S, make_smem_desc_sw128(aQ + kk * 32, 0, 1024),
                                  make_smem_desc_sw128(aK + st * TILE_BYTES + kk * 32, 0, 1024), idesc_s, kk > 0 ? 1u : 0u);
                 umma_commit(&k_empty[st]);
                 umma_commit(s_full);
-            };
-            mbar_wait(q_full, 0);
-            issue_s(0);
-            for (int j = 0; j < n_chunks; ++j) {
-                const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
-                // p_full(j): the softmax warps have read S_j completely and written P_j.  S_{j+1} goes FIRST (its columns are free), so the
-                // next chunk's softmax starts while PV_j executes.
-                mbar_wait(p_full, j & 1);
-                tc_fence_after();
-                if (j + 1 < n_chunks) issue_s(j + 1);
-                mbar_wait(&v_full[st], ph);
-                tc_fence_after();
+            }
+            __syncwarp();
+        };
+        mbar_wait(q_full, 0);
+        issue_s(0);
+        for (int j = 0; j < n_chunks; ++j) {
+            const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
+            // p_full(j): the softmax warps have read S_j completely and written P_j.  S_{j+1} goes FIRST (its columns are free), so the
+            // next chunk's softmax starts while PV_j executes.
+            mbar_wait(p_full, j & 1);
+            tc_fence_after();
+            if (j + 1 < n_chunks) issue_s(j + 1);
+            mbar_wait(&v_full[st], ph);
+            tc_fence_after();
+            if (elect_one()) {
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk)                // O += P_j V_j
                     umma_bf16_ss(tmem_O, make_smem_desc_sw128(aP + (kk >> 2) * TILE_BYTES + (kk & 3) * 32, 0, 1024),
@@ -163,11 +175,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdParam
                 umma_commit(&v_empty[st]);
                 umma_commit(pv_done);
             }
+            __syncwarp();
         }
     } else {
         // ===================== softmax warps: two threads per query row, 64 key columns each =====================
         const int q4 = warp & 3;                      // TMEM lane quarter this warp may access (hardware rule: warp id % 4)
-        const int hf = (warp - 2) >> 2;               // which 64-column half of the chunk
+        const int hf = warp >> 2;                     // which 64-column half of the chunk
         const int r = q4 * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
         const uint32_t tS = tmem_S + lane_addr + hf * 64, tO = tmem_O + lane_addr + hf * 32;
@@ -309,7 +322,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdParam
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, FWD_TMEM_COLS); }
+    if (warp == FWD_WARP_TMA) { tc_fence_after(); tmem_dealloc(tmem_base, FWD_TMEM_COLS); }
 }
 
 // =================================================================================================
@@ -319,7 +332,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdParam
 //           = 226.3 KB at S = 512 (one CTA per SM).
 //   TMEM  : dQ of all query tiles 4 x 64 | dK 64 | dV 64 | S half 64 | dP half 64 = 512 columns: every accumulator stays on chip
 //           (no atomics, no scratch in HBM, deterministic), and S / dP are produced 64 KEY COLUMNS AT A TIME so that they fit beside them.
-//   warps : 0 = TMA producer, 1 = MMA issuer, 2..17 = two compute groups of 8 warps: group g owns key half g of every pair
+//   warps : 0..15 = two compute groups of 8 warps, 16 = TMA producer, 17 = MMA issuer: group g owns key half g of every pair
 //           (thread = one query row x 32 keys).  The groups run half a pair apart, so while one computes P / dS from registers the
 //           tensor core produces the other's S / dP: v3 measured no gain from overlapping whole-tile phases because its dQ went through
 //           16 B/clk/SM of L2 atomics; v1 kept dQ on chip but had S and dP share columns, serialising every MMA behind a compute phase.
@@ -327,8 +340,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdParam
 //   MMA order per pair : S(t,0) dP(t,0) S(t,1) dV(t-1) dP(t,1) dK(t-1) dQ(t-1) -- the accumulating MMAs trail by one pair, so the issuer
 //           never blocks the next pair's S / dP behind operands (P~, dS) that the compute warps are still writing.
 // =================================================================================================
-constexpr int BWD_THREADS = 576;       // warp 0: TMA + TMEM alloc, warp 1: MMA, warps 2..17: compute
+constexpr int BWD_THREADS = 576;       // warps 0..15: compute, 16: TMA + TMEM alloc, 17: MMA issuer (highest ids: favoured by the arbiter)
 constexpr int BWD_COMPUTE_WARPS = 16;
+constexpr int BWD_WARP_TMA = 16, BWD_WARP_MMA = 17;
 constexpr int BWD_GROUP_WARPS = 8;
 constexpr int HALF_BYTES = 64 * HD * 2;    // 8 KB: 64 key rows of a K / V tile
 
@@ -414,16 +428,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         mbar_init(dv_done, 1); mbar_init(pair_done, 1); mbar_init(dkv_full, 1); mbar_init(dkv_read, BWD_COMPUTE_WARPS);
         fence_barrier_init();
     }
-    if (warp == 0) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
+    if (warp == BWD_WARP_TMA) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     const uint32_t tmem_dQ = tmem_base, tmem_dK = tmem_base + 256, tmem_dV = tmem_base + 320, tmem_S = tmem_base + 384, tmem_dP = tmem_base + 448;
 
-    if (warp == 0) {
+    // Producer and MMA warps: warp-uniform loops (all lanes wait), tcgen05 / TMA instructions under elect_one() -- see gemm_sm100.cu.
+    if (warp == BWD_WARP_TMA) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(kv_full, 2 * TILE_BYTES);
             tma_load_3d(sK, &tmap_qkv, kv_full, p.H + h * HD, 0, b);
             tma_load_3d(sV, &tmap_qkv, kv_full, 2 * p.H + h * HD, 0, b);
@@ -432,43 +447,56 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
                 tma_load_3d(sQ + i * TILE_BYTES, &tmap_qkv, &q_full[i], h * HD, i * TQ, b);
                 tma_load_3d(sdO + i * TILE_BYTES, &tmap_do, &q_full[i], h * HD, i * TQ, b);
             }
-            for (int j = 1; j < n; ++j) {
-                mbar_wait(kv_empty, (j - 1) & 1);            // every MMA that reads K_{j-1} / V_{j-1} has retired
+        }
+        __syncwarp();
+        for (int j = 1; j < n; ++j) {
+            mbar_wait(kv_empty, (j - 1) & 1);                // every MMA that reads K_{j-1} / V_{j-1} has retired
+            if (elect_one()) {
                 mbar_expect_tx(kv_full, 2 * TILE_BYTES);
                 tma_load_3d(sK, &tmap_qkv, kv_full, p.H + h * HD, j * TQ, b);
                 tma_load_3d(sV, &tmap_qkv, kv_full, 2 * p.H + h * HD, j * TQ, b);
             }
+            __syncwarp();
         }
-    } else if (warp == 1) {
+    } else if (warp == BWD_WARP_MMA) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t id_h = make_idesc_bf16(TQ, 64, false, false);      // S half, dP half: [128 q] x [64 keys], K = d
-            constexpr uint32_t id_mm = make_idesc_bf16(TQ, HD, true, true);       // dV, dK
-            constexpr uint32_t id_km = make_idesc_bf16(TQ, HD, false, true);      // dQ
-            const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ0 = smem_u32(sQ), adO0 = smem_u32(sdO), aP = smem_u32(sP), adS = smem_u32(sdS);
-            auto issue_s = [&](int i_, int g_) {                // S(t, g) = Q_i K_{j, half g}^T
+        constexpr uint32_t id_h = make_idesc_bf16(TQ, 64, false, false);      // S half, dP half: [128 q] x [64 keys], K = d
+        constexpr uint32_t id_mm = make_idesc_bf16(TQ, HD, true, true);       // dV, dK
+        constexpr uint32_t id_km = make_idesc_bf16(TQ, HD, false, true);      // dQ
+        const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ0 = smem_u32(sQ), adO0 = smem_u32(sdO), aP = smem_u32(sP), adS = smem_u32(sdS);
+        auto issue_s = [&](int i_, int g_) {                // S(t, g) = Q_i K_{j, half g}^T
+            if (elect_one()) {
                 const uint32_t aQ = aQ0 + i_ * TILE_BYTES, aKh = aK + g_ * HALF_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
                     umma_bf16_ss(tmem_S, make_smem_desc_sw128(aQ + kk * 32, 0, 1024), make_smem_desc_sw128(aKh + kk * 32, 0, 1024), id_h, kk > 0 ? 1u : 0u);
                 umma_commit(&s_full[g_]);
-            };
-            auto issue_dp = [&](int i_, int g_) {               // dP(t, g) = dO_i V_{j, half g}^T
+            }
+            __syncwarp();
+        };
+        auto issue_dp = [&](int i_, int g_) {               // dP(t, g) = dO_i V_{j, half g}^T
+            if (elect_one()) {
                 const uint32_t adO = adO0 + i_ * TILE_BYTES, aVh = aV + g_ * HALF_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
                     umma_bf16_ss(tmem_dP, make_smem_desc_sw128(adO + kk * 32, 0, 1024), make_smem_desc_sw128(aVh + kk * 32, 0, 1024), id_h, kk > 0 ? 1u : 0u);
                 umma_commit(&dp_full[g_]);
-            };
-            auto issue_dv = [&](int i_) {                       // dV_j += P~^T dO_i
+            }
+            __syncwarp();
+        };
+        auto issue_dv = [&](int i_) {                       // dV_j += P~^T dO_i
+            if (elect_one()) {
                 const uint32_t adO = adO0 + i_ * TILE_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk)
                     umma_bf16_ss(tmem_dV, make_smem_desc_sw128(aP + kk * 2048, TILE_BYTES, 1024),
                                  make_smem_desc_sw128(adO + kk * 2048, TILE_BYTES, 1024), id_mm, (i_ > 0 || kk > 0) ? 1u : 0u);
                 umma_commit(dv_done);
-            };
-            auto issue_dkdq = [&](int i_, int j_) {             // dK_j += dS^T Q_i ; dQ_i += dS K_j
+            }
+            __syncwarp();
+        };
+        auto issue_dkdq = [&](int i_, int j_) {             // dK_j += dS^T Q_i ; dQ_i += dS K_j
+            if (elect_one()) {
                 const uint32_t aQ = aQ0 + i_ * TILE_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk)
@@ -479,40 +507,44 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
                     umma_bf16_ss(tmem_dQ + i_ * HD, make_smem_desc_sw128(adS + (kk >> 2) * TILE_BYTES + (kk & 3) * 32, 0, 1024),
                                  make_smem_desc_sw128(aK + kk * 2048, TILE_BYTES, 1024), id_km, (j_ > 0 || kk > 0) ? 1u : 0u);
                 umma_commit(pair_done);
-            };
-            auto wait = [&](uint64_t* bar, int phase) { mbar_wait(bar, (uint32_t)phase & 1u); tc_fence_after(); };
-            for (int j = 0; j < n; ++j) {
-                wait(kv_full, j);
-                if (j >= 1) wait(dkv_read, j - 1);              // dK / dV accumulators of the previous kv tile drained
-                for (int i = 0; i < n; ++i) {
-                    const int t = j * n + i;
-                    if (j == 0) wait(&q_full[i], 0);
-                    if (t >= 1) wait(&s_free[1], t - 1);        // group 1 has S(t-1, 1) in registers: the S columns are free
-                    issue_s(i, 0);
-                    if (t >= 1) wait(&dp_free[1], t - 1);
-                    issue_dp(i, 0);
-                    wait(&s_free[0], t);
-                    issue_s(i, 1);
-                    if (i >= 1) { wait(p_full, t - 1); issue_dv(i - 1); }
-                    wait(&dp_free[0], t);
-                    issue_dp(i, 1);
-                    if (i >= 1) { wait(ds_full, t - 1); issue_dkdq(i - 1, j); }
-                }
-                const int tl = j * n + n - 1;                   // the trailing pair of this kv tile
-                wait(p_full, tl); issue_dv(n - 1);
-                wait(ds_full, tl); issue_dkdq(n - 1, j);
+            }
+            __syncwarp();
+        };
+        auto wait = [&](uint64_t* bar, int phase) { mbar_wait(bar, (uint32_t)phase & 1u); tc_fence_after(); };
+        for (int j = 0; j < n; ++j) {
+            wait(kv_full, j);
+            if (j >= 1) wait(dkv_read, j - 1);              // dK / dV accumulators of the previous kv tile drained
+            for (int i = 0; i < n; ++i) {
+                const int t = j * n + i;
+                if (j == 0) wait(&q_full[i], 0);
+                if (t >= 1) wait(&s_free[1], t - 1);        // group 1 has S(t-1, 1) in registers: the S columns are free
+                issue_s(i, 0);
+                if (t >= 1) wait(&dp_free[1], t - 1);
+                issue_dp(i, 0);
+                wait(&s_free[0], t);
+                issue_s(i, 1);
+                if (i >= 1) { wait(p_full, t - 1); issue_dv(i - 1); }
+                wait(&dp_free[0], t);
+                issue_dp(i, 1);
+                if (i >= 1) { wait(ds_full, t - 1); issue_dkdq(i - 1, j); }
+            }
+            const int tl = j * n + n - 1;                   // the trailing pair of this kv tile
+            wait(p_full, tl); issue_dv(n - 1);
+            wait(ds_full, tl); issue_dkdq(n - 1, j);
+            if (elect_one()) {
                 umma_commit(kv_empty);
                 umma_commit(dkv_full);
             }
+            __syncwarp();
         }
     } else {
         // ===================== compute warps =====================
         const int q4 = warp & 3;                                // TMEM lane quarter (hardware rule: warp id % 4)
-        const int wi = (warp - 2) >> 2;                         // 0..3
+        const int wi = warp >> 2;                               // 0..3
         const int g = wi >> 1, c = wi & 1;                      // key half of the pair this warp's group owns; 32-column half of that
         const int r = q4 * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
-        const int ct = threadIdx.x - 64;
+        const int ct = threadIdx.x;
         for (int i = ct; i < S; i += BWD_COMPUTE_WARPS * 32) sMask[i] = p.mask ? p.mask[(long long)b * S + i] * LOG2E : 0.f;
         named_bar_sync(1, BWD_COMPUTE_WARPS * 32);
         const long long bh = (long long)b * p.A + h;
@@ -659,7 +691,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+    if (warp == BWD_WARP_TMA) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 }  // namespace dle

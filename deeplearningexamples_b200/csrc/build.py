@@ -39,6 +39,25 @@ def _compile(src):
     return obj, False
 
 
+def build_variant(name, extra_flags):
+    """A/B builds of the same ABI with different compile-time switches (e.g. -DDLE_MBAR_HINT_NS=0): deeplearningexamples_b200/libdle_b200_<name>.so,
+    selected at run time with DLE_LIB_PATH (see _lib.py).  Measurement tooling only."""
+    vdir = os.path.join(OBJ_DIR, "variant_" + name)
+    os.makedirs(vdir, exist_ok=True)
+    objs = []
+    for src in SOURCES:
+        obj = os.path.join(vdir, src.replace(".cu", ".o"))
+        r = subprocess.run([NVCC] + FLAGS + list(extra_flags) + ["-c", os.path.join(HERE, src), "-o", obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+        objs.append(obj)
+    out = os.path.join(PKG, "libdle_b200_%s.so" % name)
+    r = subprocess.run([NVCC, "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return out
+
+
 def build(force=False, verbose=False):
     os.makedirs(OBJ_DIR, exist_ok=True)
     if force:
@@ -59,3 +78,5 @@ def build(force=False, verbose=False):
 
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose=True)
+    if "--variant-nohint" in sys.argv:
+        print("built", build_variant("nohint", ["-DDLE_MBAR_HINT_NS=0"]))

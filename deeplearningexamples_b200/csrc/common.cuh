@@ -67,6 +67,38 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2 / FMUL2: one issue slot for two lanes of work) and byte permute
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pack_f32x2(a0, a1)), "l"(pack_f32x2(b0, b1)), "l"(pack_f32x2(c0, c1)));
+    unpack_f32x2(d, d0, d1);
+}
+__device__ __forceinline__ void fmul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pack_f32x2(a0, a1)), "l"(pack_f32x2(b0, b1)));
+    unpack_f32x2(d, d0, d1);
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pack_f32x2(a0, a1)), "l"(pack_f32x2(b0, b1)));
+    unpack_f32x2(d, d0, d1);
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
 // math: tanh-GELU (reference modeling.py:121-122, approximate=True == tanh form)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -78,6 +110,32 @@ __device__ __forceinline__ float gelu_tanh(float x) {
     const float c = 0.7978845608028654f;
     float t = tanh_fast(c * (x + 0.044715f * x * x * x));
     return 0.5f * x * (1.0f + t);
+}
+// two lanes at a time on the packed-fp32 pipe (FMUL2 / FFMA2): 0.5 x (1 + tanh(c x (1 + 0.044715 x^2)))
+__device__ __forceinline__ void gelu_tanh2(float x0, float x1, float& y0, float& y1) {
+    const float c0 = 0.7978845608028654f, c1 = 0.7978845608028654f * 0.044715f;
+    float s0, s1, a0, a1, h0, h1;
+    fmul2(s0, s1, x0, x1, x0, x1);
+    ffma2(s0, s1, s0, s1, c1, c1, c0, c0);
+    fmul2(a0, a1, x0, x1, s0, s1);
+    const float t0 = tanh_fast(a0), t1 = tanh_fast(a1);
+    fmul2(h0, h1, x0, x1, 0.5f, 0.5f);
+    ffma2(y0, y1, h0, h1, t0, t1, h0, h1);
+}
+// d/dx of the above for two lanes: 0.5 (1 + t) + 0.5 x (1 - t^2) c (1 + 3 * 0.044715 x^2),  t = tanh(c x (1 + 0.044715 x^2))
+__device__ __forceinline__ void gelu_tanh_grad2(float x0, float x1, float& y0, float& y1) {
+    const float c0 = 0.7978845608028654f, c1 = 0.7978845608028654f * 0.044715f, c3 = 3.0f * 0.7978845608028654f * 0.044715f;
+    float s0, s1, i0, i1, a0, a1, d0, d1, q0, q1, h0, h1, r0, r1, g0, g1;
+    fmul2(s0, s1, x0, x1, x0, x1);
+    ffma2(i0, i1, s0, s1, c1, c1, c0, c0);
+    fmul2(a0, a1, x0, x1, i0, i1);
+    const float t0 = tanh_fast(a0), t1 = tanh_fast(a1);
+    ffma2(d0, d1, -t0, -t1, t0, t1, 1.0f, 1.0f);            // 1 - t^2
+    ffma2(q0, q1, s0, s1, c3, c3, c0, c0);                  // c (1 + 3 * 0.044715 x^2)
+    fmul2(h0, h1, x0, x1, 0.5f, 0.5f);
+    fmul2(r0, r1, h0, h1, d0, d1);
+    ffma2(g0, g1, t0, t1, 0.5f, 0.5f, 0.5f, 0.5f);          // 0.5 (1 + t)
+    ffma2(y0, y1, r0, r1, q0, q1, g0, g1);
 }
 __device__ __forceinline__ float gelu_tanh_grad(float x) {
     const float c = 0.7978845608028654f;
@@ -158,38 +216,6 @@ __device__ __forceinline__ unsigned long long effective_seed(unsigned long long 
 }
 
 // ---------------------------------------------------------------------------------------------
-// packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2 / FMUL2: one issue slot for two lanes of work) and byte permute
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& lo, float& hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
-    unsigned long long d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pack_f32x2(a0, a1)), "l"(pack_f32x2(b0, b1)), "l"(pack_f32x2(c0, c1)));
-    unpack_f32x2(d, d0, d1);
-}
-__device__ __forceinline__ void fmul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
-    unsigned long long d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pack_f32x2(a0, a1)), "l"(pack_f32x2(b0, b1)));
-    unpack_f32x2(d, d0, d1);
-}
-__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
-    unsigned long long d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pack_f32x2(a0, a1)), "l"(pack_f32x2(b0, b1)));
-    unpack_f32x2(d, d0, d1);
-}
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
-    uint32_t r;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
-    return r;
-}
-
-// ---------------------------------------------------------------------------------------------
 // Attention-probability dropout (forward and backward of the fused attention kernels): keep decisions for the 32 consecutive
 // elements of group `group32`, delivered as 16 AND-masks for packed bf16x2 pairs (mask[i] covers elements 2i | 2i+1: 0xFFFF per kept
 // half) -- P~ = P & mask costs one LOP3 per pair instead of a bit extract + select per element.
@@ -240,14 +266,26 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // for issue slots with the softmax warps of the same SM sub-partition.
 // Watchdog: a wait that has not completed after 4 s of wall clock (kernels here last milliseconds) is a protocol bug; trap so the
 // launch fails with an error instead of hanging the GPU.
+#ifndef DLE_MBAR_HINT_NS
+#define DLE_MBAR_HINT_NS 0x989680          /* 10 ms; 0 = no suspend-time hint (hardware default time limit per try_wait) */
+#endif
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t addr, uint32_t parity) {
     uint32_t ok;
+#if DLE_MBAR_HINT_NS
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
         "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, P1;\n"
-        "}\n" : "=r"(ok) : "r"(addr), "r"(parity), "r"(0x989680u) : "memory");
+        "}\n" : "=r"(ok) : "r"(addr), "r"(parity), "r"((uint32_t)DLE_MBAR_HINT_NS) : "memory");
+#else
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+#endif
     return ok;
 }
 __device__ __forceinline__ unsigned long long global_timer_ns() {

@@ -21,7 +21,9 @@ namespace dle {
 constexpr int BM = 128;
 constexpr int BK = 64;        // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 384;      // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
+constexpr int GEMM_THREADS = 384;      // warps 0..7 epilogue, 8 TMA, 9 MMA, 10 TMEM alloc, 11 spare.  The single-issuer warps carry the HIGHEST
+                                       // warp ids: the SM sub-partition arbiter favours higher warp ids, and a starved MMA issuer idles the tensor pipe
+constexpr int WARP_TMA = 8, WARP_MMA = 9, WARP_ALLOC = 10;
 constexpr int GEMM_EPI_THREADS = 256;
 
 template <int BN> struct GemmCfg {
@@ -179,7 +181,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
         // pre-activation so that backward (which only has the stored bf16 u) differentiates what forward evaluated.
         warp_store_rows(p.out2, p.ldo2, row_base, col0, p.M, p.N, stage, lane, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = gelu_tanh(__bfloat162float(__float2bfloat16_rn(v[i])));
+        for (int i = 0; i < 32; i += 2) {
+            const uint32_t u2 = pack_bf16(v[i], v[i + 1]);       // the bf16 pair just stored
+            gelu_tanh2(__uint_as_float(u2 << 16), __uint_as_float(u2 & 0xFFFF0000u), v[i], v[i + 1]);
+        }
     } else if (p.epilogue == DLE_EPI_BIAS_DROPOUT_RESIDUAL) {
         if (p.drop_thresh != 0) {
             const uint32_t keep = dropout_keep32(seed, p.drop_stream, (unsigned long long)(row * (long long)p.N + col0) >> 5, p.drop_thresh);
@@ -201,7 +206,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
             float a[8];                                     // stored pre-activation u
             unpack8(aux[c], a);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[c * 8 + k] *= gelu_tanh_grad(a[k]);
+            for (int k = 0; k < 8; k += 2) {
+                float g0, g1;
+                gelu_tanh_grad2(a[k], a[k + 1], g0, g1);
+                fmul2(v[c * 8 + k], v[c * 8 + k + 1], v[c * 8 + k], v[c * 8 + k + 1], g0, g1);
+            }
         }
     } else if (p.epilogue == DLE_EPI_ADD) {
 #pragma unroll
@@ -253,7 +262,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], GEMM_EPI_THREADS / 32); }
         fence_barrier_init();
     }
-    if (warp == 2) { tmem_alloc(tmem_ptr, Cfg::TMEM_COLS); tmem_relinquish(); }
+    if (warp == WARP_ALLOC) { tmem_alloc(tmem_ptr, Cfg::TMEM_COLS); tmem_relinquish(); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -262,16 +271,20 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int total_units = p.m_tiles * p.n_tiles * p.splits;
     const int kb_per_split = (p.kb_total + p.splits - 1) / p.splits;
 
-    if (warp == 0) {
+    // The producer and MMA warps run their loops WARP-UNIFORMLY (all 32 lanes wait on the barriers) and only the tcgen05 / TMA
+    // instructions sit under elect_one(): inside an `if (lane == 0)` region ptxas cannot keep descriptors and addresses in uniform
+    // registers and wraps every UTCHMMA / UTMALDG in an ELECT + R2UR + BRA.U.ANY waterfall (11-16 instructions per MMA, measured on the
+    // attention kernels as an MMA-issue-bound tensor pipe at 18 %); warp-uniform flow issues consecutive MMAs back to back.
+    if (warp == WARP_TMA) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-                const int tile = unit / p.splits, split = unit - tile * p.splits;
-                const int m_blk = tile / p.n_tiles, n_blk = tile - m_blk * p.n_tiles;
-                const int kb0 = split * kb_per_split, kb1 = min(p.kb_total, kb0 + kb_per_split);
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+        int stage = 0; uint32_t phase = 0;
+        for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+            const int tile = unit / p.splits, split = unit - tile * p.splits;
+            const int m_blk = tile / p.n_tiles, n_blk = tile - m_blk * p.n_tiles;
+            const int kb0 = split * kb_per_split, kb1 = min(p.kb_total, kb0 + kb_per_split);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
                     mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + Cfg::A_BYTES;
@@ -289,26 +302,28 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         for (int g = 0; g < BN / 64; ++g)
                             tma_load_2d(sb + g * (BK * 128), &tmap_b, &full_bar[stage], n_blk * BN + g * 64, kb * BK);
                     }
-                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer (single thread) =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
-            int stage = 0; uint32_t phase = 0; int it = 0;
-            for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
-                const int split = unit % p.splits;
-                const int kb0 = split * kb_per_split, kb1 = min(p.kb_total, kb0 + kb_per_split);
-                const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    } else if (warp == WARP_MMA) {
+        // ===================== MMA issuer (one elected lane issues; the warp waits together) =====================
+        constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+        int stage = 0; uint32_t phase = 0; int it = 0;
+        const uint32_t smem_base = smem_u32(smem);
+        for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
+            const int split = unit % p.splits;
+            const int kb0 = split * kb_per_split, kb1 = min(p.kb_total, kb0 + kb_per_split);
+            const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
+            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * BN;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * BN;
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                if (elect_one()) {
+                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                     const uint32_t sb = sa + Cfg::A_BYTES;
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -322,17 +337,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                         umma_bf16_ss(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);      // frees this smem stage when the MMAs retire
-                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                    if (kb + 1 == kb1) umma_commit(&tmem_full[acc]);     // accumulator complete -> epilogue
                 }
-                umma_commit(&tmem_full[acc]);            // accumulator complete -> epilogue
+                __syncwarp();
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (kb1 <= kb0) {                            // (cannot happen: the launcher never creates an empty split) keep the epilogue's wait finite
+                if (elect_one()) umma_commit(&tmem_full[acc]);
+                __syncwarp();
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp < 8) {
         // ===================== epilogue warps (TMEM -> registers -> global) =====================
-        const int q = warp & 3;                          // TMEM lane quarter this warp may access
-        const int half = (warp - 4) >> 2;                // two warps share a quarter: each drains half the columns
+        const int q = warp & 3;                          // TMEM lane quarter this warp may access (hardware rule: warp id % 4)
+        const int half = warp >> 2;                      // two warps share a quarter: each drains half the columns
         constexpr int CH = BN / 64;                      // chunks per warp per tile
-        const uint32_t out_tile = smem_u32(epi_stage) + (warp - 4) * 2 * EPI_TILE_BYTES;
+        const uint32_t out_tile = smem_u32(epi_stage) + warp * 2 * EPI_TILE_BYTES;
         const uint32_t aux_tile = out_tile + EPI_TILE_BYTES;
         const unsigned long long seed = (p.drop_thresh != 0u) ? effective_seed(p.seed, p.seed_dev) : 0ull;
         const bool use_aux = p.aux != nullptr && (p.epilogue == DLE_EPI_BIAS_DROPOUT_RESIDUAL || p.epilogue == DLE_EPI_DGELU ||
@@ -410,7 +430,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+    if (warp == WARP_ALLOC) { tc_fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -445,15 +465,16 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
     return r == CUDA_SUCCESS ? DLE_OK : DLE_ERR_CUDA;
 }
 
-static int g_num_sms = 0;
 static int num_sms() {
-    if (g_num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
+    static int sms[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 148;
+    if (sms[dev] == 0) {
+        cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (sms[dev] <= 0) sms[dev] = 148;
     }
-    return g_num_sms;
+    return sms[dev];
 }
 
 template <int BN, bool A_MN, bool B_MN>
@@ -493,11 +514,13 @@ static int launch_gemm(const dle_gemm_args* a, cudaStream_t stream) {
     p.colsum_out = reinterpret_cast<float*>(a->colsum_out);
 
     auto kern = gemm_bf16_tcgen05_kernel<BN, A_MN, B_MN>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};                      // the attribute is per device (and per template instance)
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return DLE_ERR_CUDA;
+    if (!attr_set[dev]) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
             return DLE_ERR_CUDA;
-        attr_set = true;
+        attr_set[dev] = true;
     }
     const int units = p.m_tiles * p.n_tiles * p.splits;
     const int grid = units < num_sms() ? units : num_sms();
@@ -520,7 +543,10 @@ extern "C" int dle_gemm_bf16(const dle_gemm_args* a, void* stream_) {
     if (a->epilogue == DLE_EPI_BIAS_DROPOUT_RESIDUAL && a->dropout_p > 0.f) DLE_CHECK_ARG(a->N % 32 == 0);   // 32-element RNG groups
     if (a->epilogue == DLE_EPI_BIAS_GELU) DLE_CHECK_ARG(a->out2 != nullptr && a->ldo2 % 8 == 0);
     if (a->epilogue == DLE_EPI_DGELU || a->epilogue == DLE_EPI_ADD) DLE_CHECK_ARG(a->aux != nullptr);
-    if (a->aux != nullptr) DLE_CHECK_ARG(a->ld_aux % 8 == 0);
+    if (a->aux != nullptr) DLE_CHECK_ARG(a->ld_aux % 8 == 0 && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0);
+    // the epilogue reads the bias slice with 4- / 8-byte loads and stores 16-byte vectors
+    DLE_CHECK_ARG((reinterpret_cast<uintptr_t>(a->bias) & 7) == 0 && (reinterpret_cast<uintptr_t>(a->out) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(a->out2) & 15) == 0);
     const bool amn = a->a_layout == DLE_LAYOUT_MN, bmn = a->b_layout == DLE_LAYOUT_MN;
     // narrow-N problems (and the small-tile preference flag) take the 128-wide tile
     const bool bn128 = (a->N <= 128) || (a->tile_n == 128);

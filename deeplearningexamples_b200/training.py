@@ -151,7 +151,8 @@ def capture_step_graph(fn, warmup_iters=11):
             fn()
     torch.cuda.current_stream().wait_stream(side)
     graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
+    # thread_local: CUDA calls made by OTHER host threads during the capture (NCCL watchdog, data-loader pinning) must not invalidate it
+    with torch.cuda.graph(graph, capture_error_mode="thread_local"):
         fn()
     return graph
 

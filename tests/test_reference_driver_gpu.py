@@ -65,7 +65,10 @@ def test_installed_reference_script_is_the_reference_file():
 def test_unmodified_reference_driver_trains_checkpoints_and_resumes_over_the_b200_mirror(tmp_path, graphs):
     _need_ref()
     out = tmp_path / "results"
-    extra = ["--cuda_graphs"] if graphs else []
+    # the reference's own --cuda_graphs cannot capture its dense-sequence-output path (torch.nonzero at modeling.py:590 and the boolean
+    # label indexing of ITS criterion, run_pretraining.py:89, synchronise): like the reference model itself, the mirror is driven with
+    # the script's --no_dense_sequence_output when graphs are on
+    extra = ["--cuda_graphs", "--no_dense_sequence_output"] if graphs else []
     r, recs = _run("ours", out, extra, 10, tmp_path)
     assert os.path.exists(out / "ckpt_10.pt") and os.path.exists(out / "ckpt_5.pt")
     assert _final(recs, "training_sequences_per_second") > 0

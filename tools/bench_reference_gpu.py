@@ -78,7 +78,9 @@ def main():
     if not a.jit:
         argv += ["--disable_jit_fusions"]
     if a.cuda_graphs:
-        argv += ["--cuda_graphs"]
+        # the reference's graph mode only captures with --no_dense_sequence_output: its dense path calls torch.nonzero (modeling.py:590)
+        # and its criterion indexes labels with a boolean mask (run_pretraining.py:89), both of which synchronise
+        argv += ["--cuda_graphs", "--no_dense_sequence_output"]
     sys.argv = argv
     spec = importlib.util.spec_from_file_location("run_pretraining", script)
     rp = importlib.util.module_from_spec(spec)
