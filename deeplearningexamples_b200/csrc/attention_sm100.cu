@@ -78,7 +78,7 @@ struct AttnFwdParams {
 __global__ void __launch_bounds__(FWD_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int S = p.S, n_chunks = S / TQ;
+    const int S = p.S;
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + TILE_BYTES;               // [2]
     uint8_t* sV = sK + 2 * TILE_BYTES;           // [2]
@@ -94,6 +94,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdParam
     uint64_t* p_full = bars + 10;        // 1 (one arrival per softmax warp)
     uint64_t* pv_done = bars + 11;       // 1
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+    int* s_nk = reinterpret_cast<int*>(bars + 12) + 1;     // number of key chunks that hold at least one attendable key
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -105,13 +106,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdParam
         for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
         mbar_init(s_full, 1); mbar_init(p_full, FWD_SOFTMAX_WARPS); mbar_init(pv_done, 1);
         fence_barrier_init();
+        *s_nk = 0;
     }
     if (warp == FWD_WARP_TMA) { tmem_alloc(tmem_ptr, FWD_TMEM_COLS); tmem_relinquish(); }
+    // Variable-length batches: trailing key chunks whose additive mask is <= -1000 for EVERY key contribute exp2(..) == 0 exactly in
+    // fp32 (the running maximum comes from an attendable key), so they are skipped outright -- no load, no MMA, no softmax -- and the
+    // result is bit-identical to processing them (padding-skipping of FasterTransformer-style inference; it also
+    // applies to training on LDDL's binned, partly padded batches).
+    if (p.mask != nullptr) {
+        __syncthreads();
+        int last = 0;
+        for (int k = threadIdx.x; k < S; k += FWD_THREADS)
+            if (__ldg(p.mask + (long long)b * S + k) > -1000.0f) last = k / TQ + 1;
+        last = __reduce_max_sync(0xffffffffu, last);
+        if (lane == 0 && last > 0) atomicMax(s_nk, last);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + TQ;
+    const int n_all = S / TQ;
+    const int n_chunks = (p.mask != nullptr && *s_nk > 0) ? *s_nk : n_all;
 
     // Producer and MMA warps: warp-uniform loops (all lanes wait), tcgen05 / TMA instructions under elect_one() -- see gemm_sm100.cu.
     if (warp == FWD_WARP_TMA) {
@@ -411,6 +427,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     uint64_t* dkv_full = bars + 18;   // kv tile finished: dK, dV (and at the end dQ) complete
     uint64_t* dkv_read = bars + 19;   // accumulators drained (16)
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
+    int* s_nk = reinterpret_cast<int*>(bars + 20) + 1;      // kv tiles that hold at least one attendable key
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = blockIdx.x, b = blockIdx.y;
@@ -427,11 +444,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         mbar_init(p_full, BWD_COMPUTE_WARPS); mbar_init(ds_full, BWD_COMPUTE_WARPS);
         mbar_init(dv_done, 1); mbar_init(pair_done, 1); mbar_init(dkv_full, 1); mbar_init(dkv_read, BWD_COMPUTE_WARPS);
         fence_barrier_init();
+        *s_nk = 0;
     }
     if (warp == BWD_WARP_TMA) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
+    // trailing kv tiles that are masked out for every key (additive mask <= -1000) have P == 0 exactly: dK = dV = 0 there and dQ gets
+    // nothing from them, so they are skipped and their dK / dV rows are written as zeros (bit-identical to computing them)
+    if (p.mask != nullptr) {
+        __syncthreads();
+        int last = 0;
+        for (int k = threadIdx.x; k < S; k += BWD_THREADS)
+            if (__ldg(p.mask + (long long)b * S + k) > -1000.0f) last = k / TQ + 1;
+        last = __reduce_max_sync(0xffffffffu, last);
+        if (lane == 0 && last > 0) atomicMax(s_nk, last);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    const int nk = (p.mask != nullptr && *s_nk > 0) ? *s_nk : n;
     const uint32_t tmem_base = *tmem_ptr;
     const uint32_t tmem_dQ = tmem_base, tmem_dK = tmem_base + 256, tmem_dV = tmem_base + 320, tmem_S = tmem_base + 384, tmem_dP = tmem_base + 448;
 
@@ -449,7 +478,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             }
         }
         __syncwarp();
-        for (int j = 1; j < n; ++j) {
+        for (int j = 1; j < nk; ++j) {
             mbar_wait(kv_empty, (j - 1) & 1);                // every MMA that reads K_{j-1} / V_{j-1} has retired
             if (elect_one()) {
                 mbar_expect_tx(kv_full, 2 * TILE_BYTES);
@@ -511,7 +540,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             __syncwarp();
         };
         auto wait = [&](uint64_t* bar, int phase) { mbar_wait(bar, (uint32_t)phase & 1u); tc_fence_after(); };
-        for (int j = 0; j < n; ++j) {
+        for (int j = 0; j < nk; ++j) {
             wait(kv_full, j);
             if (j >= 1) wait(dkv_read, j - 1);              // dK / dV accumulators of the previous kv tile drained
             for (int i = 0; i < n; ++i) {
@@ -552,7 +581,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         const unsigned long long seed = effective_seed(p.seed, p.seed_dev);
         const int kc = g * 64 + c * 32;                         // first key column (within the 128-key tile) of this thread
         const float c1 = p.drop_scale * p.scale;
-        for (int j = 0; j < n; ++j) {
+        for (int j = 0; j < nk; ++j) {
             // my 32 key columns of this kv tile: additive mask (already x log2e) from shared memory, skipped entirely when it is all
             // zero (warp-uniform; unpadded batches)
             const uint32_t mk_addr = smem_u32(sMask + j * TQ + kc);
@@ -667,6 +696,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(dkv_read);
+        }
+        // ---- skipped (fully masked) kv tiles: zero dK / dV rows
+        for (int j = nk; j < n; ++j) {
+            const long long tok = (long long)b * p.tok_stride_b + (long long)(j * TQ + r) * p.tok_stride_s;
+            bf16* o = p.dqkv + tok * (3LL * p.H) + (g + 1) * p.H + h * HD + c * 32;
+#pragma unroll
+            for (int k = 0; k < 32; k += 8) st_global_v4(o + k, 0u, 0u, 0u, 0u);
         }
         // ---- all pairs done (dkv_full of the last kv tile implies every MMA retired): drain dQ, two 32-column chunks per warp
         for (int ch = wi; ch < 2 * n; ch += 4) {

@@ -20,3 +20,4 @@ for cfg in "32 --cuda-graphs" "64 " "64 --cuda-graphs"; do
   timeout -k 10 600 python tools/bench_reference_gpu.py --arm reference --batch $1 --steps 6 $2 > gpurun_out/r2_3_ref_$tag.json 2> gpurun_out/r2_3_ref_$tag.err; echo "ref $tag rc=$?"; grep "host enqueue" gpurun_out/r2_3_ref_$tag.err; cut -c1-330 gpurun_out/r2_3_ref_$tag.json
 done
 timeout -k 10 600 python tools/bench_reference_gpu.py --arm ours --batch 32 --steps 6 --cuda-graphs > gpurun_out/r2_3_ours_via_ref_b32_graphs.json 2> gpurun_out/r2_3_ours_via_ref_b32_graphs.err; echo "ours-via-ref rc=$?"; grep "host enqueue" gpurun_out/r2_3_ours_via_ref_b32_graphs.err; cut -c1-330 gpurun_out/r2_3_ours_via_ref_b32_graphs.json
+timeout -k 10 600 python tools/bench_infer.py > gpurun_out/r2_3_infer.log 2>&1; tail -6 gpurun_out/r2_3_infer.log | cut -c1-300
