@@ -264,7 +264,14 @@ def run_ours(args):
             # whole-step capture under DDP: NCCL's async error handling must be off, as the reference sets it (run_pretraining.py:334-335)
             os.environ.setdefault("NCCL_ASYNC_ERROR_HANDLING", "0")
             os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
+        # record what NCCL sets up (algorithms, channels, NVLS) without touching stdout: rank 0 writes its INIT log to a file
+        nccl_log = None
+        if rank == 0 and "NCCL_DEBUG" not in os.environ:
+            nccl_log = f"/tmp/dle_nccl_init_{os.getpid()}.log"
+            os.environ.update(NCCL_DEBUG="INFO", NCCL_DEBUG_SUBSYS="INIT,ENV,TUNING", NCCL_DEBUG_FILE=nccl_log)
         dist.init_process_group(backend="nccl", init_method="env://", device_id=device)
+    else:
+        nccl_log = None
     L.load()
     cfg, S, B, P = workload(args)
     if args.no_dropout:
@@ -443,6 +450,14 @@ def run_ours(args):
     line["config"]["cuda_graphs"] = bool(use_graphs)
     if clocks is not None:
         line["clocks"] = clocks
+    if nccl_log and os.path.exists(nccl_log):
+        keep = [l.strip() for l in open(nccl_log, errors="replace") if any(k in l for k in ("NVLS", "Channel", "channels", "Connected", "NCCL version", "nRanks", "nranks", "Algo", "threadThresholds", "P2P", "NCCL_"))]
+        brief = [l.split("NCCL INFO", 1)[-1].strip()[:160] for l in keep]
+        summary = {"nvls": any("NVLS" in l for l in brief), "lines": len(brief), "tail": brief[-12:],
+                   "channels": next((l for l in reversed(brief) if "channels" in l.lower() or "coll channels" in l.lower()), None)}
+        line["nccl"] = summary
+        for l in brief[-25:]:
+            log("  nccl: " + l)
     if rank == 0 and n == 1 and not args.no_cpu_baseline and not squad:
         del model, opt
         torch.cuda.empty_cache()

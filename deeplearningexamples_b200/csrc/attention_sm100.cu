@@ -60,9 +60,10 @@ constexpr int FWD_THREADS = (2 + FWD_SOFTMAX_WARPS) * 32;      // 320: warps 0..
 constexpr int FWD_WARP_TMA = FWD_SOFTMAX_WARPS, FWD_WARP_MMA = FWD_SOFTMAX_WARPS + 1;      // the arbiter favours them over the softmax warps)
 constexpr int FWD_TMEM_COLS = 256;
 constexpr int FWD_XCHG_BYTES = 2 * TQ * 2;                     // [half][row] bf16
-constexpr int FWD_BAR_BYTES = 128;
+constexpr int FWD_BAR_BYTES = 160;
 constexpr int FWD_SMEM_BYTES = TILE_BYTES /*Q*/ + 4 * TILE_BYTES /*K,V rings*/ + PT_BYTES /*P*/ + FWD_XCHG_BYTES + FWD_BAR_BYTES;
 constexpr float FWD_RESCALE_THRESH = 8.0f;                     // log2 domain
+constexpr int HALF_BYTES = 64 * HD * 2;                        // 8 KB: 64 key rows of a K / V tile
 
 struct AttnFwdParams {
     const float* mask;     // [B,S] additive or null
@@ -75,10 +76,13 @@ struct AttnFwdParams {
     uint32_t drop_on; float drop_scale; uint32_t drop_stream; unsigned long long seed; const unsigned long long* seed_dev;
 };
 
+// S is produced in two 64-key halves (one N = 64 MMA group per softmax half) and each half's TMEM columns are handed back as soon as the
+// owning warps hold them in registers for the exponentials (s_free): S_{j+1} is then computed by the tensor core WHILE chunk j's
+// exponentials run, instead of after them (v3a: 20 % of all stall samples were the softmax warps waiting for S).
 __global__ void __launch_bounds__(FWD_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int S = p.S;
+    const int S = p.S, n_all = S / TQ;
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + TILE_BYTES;               // [2]
     uint8_t* sV = sK + 2 * TILE_BYTES;           // [2]
@@ -90,11 +94,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdParam
     uint64_t* k_empty = bars + 3;        // [2]
     uint64_t* v_full = bars + 5;         // [2]
     uint64_t* v_empty = bars + 7;        // [2]
-    uint64_t* s_full = bars + 9;         // 1
-    uint64_t* p_full = bars + 10;        // 1 (one arrival per softmax warp)
-    uint64_t* pv_done = bars + 11;       // 1
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
-    int* s_nk = reinterpret_cast<int*>(bars + 12) + 1;     // number of key chunks that hold at least one attendable key
+    uint64_t* s_full = bars + 9;         // [2]  S half hf complete in TMEM
+    uint64_t* s_free = bars + 11;        // [2]  the 4 warps of half hf hold it in registers (one arrival per warp)
+    uint64_t* p_full = bars + 13;        // P_j complete in smem (one arrival per softmax warp)
+    uint64_t* pv_done = bars + 14;       // PV_j retired
+    uint64_t* nk_ready = bars + 15;      // the number of key chunks to process is known (one arrival per softmax warp)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
+    int* s_nk = reinterpret_cast<int*>(bars + 16) + 1;     // number of key chunks that hold at least one attendable key
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -103,31 +109,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdParam
         if ((smem_u32(smem) & 1023u) != 0) __trap();          // SWIZZLE_128B tiles need a 1024-byte aligned base
         tma_prefetch_desc(&tmap_qkv);
         mbar_init(q_full, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-        mbar_init(s_full, 1); mbar_init(p_full, FWD_SOFTMAX_WARPS); mbar_init(pv_done, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+            mbar_init(&s_full[i], 1); mbar_init(&s_free[i], FWD_SOFTMAX_WARPS / 2);
+        }
+        mbar_init(p_full, FWD_SOFTMAX_WARPS); mbar_init(pv_done, 1); mbar_init(nk_ready, FWD_SOFTMAX_WARPS);
         fence_barrier_init();
         *s_nk = 0;
     }
     if (warp == FWD_WARP_TMA) { tmem_alloc(tmem_ptr, FWD_TMEM_COLS); tmem_relinquish(); }
-    // Variable-length batches: trailing key chunks whose additive mask is <= -1000 for EVERY key contribute exp2(..) == 0 exactly in
-    // fp32 (the running maximum comes from an attendable key), so they are skipped outright -- no load, no MMA, no softmax -- and the
-    // result is bit-identical to processing them (padding-skipping of FasterTransformer-style inference; it also
-    // applies to training on LDDL's binned, partly padded batches).
-    if (p.mask != nullptr) {
-        __syncthreads();
-        int last = 0;
-        for (int k = threadIdx.x; k < S; k += FWD_THREADS)
-            if (__ldg(p.mask + (long long)b * S + k) > -1000.0f) last = k / TQ + 1;
-        last = __reduce_max_sync(0xffffffffu, last);
-        if (lane == 0 && last > 0) atomicMax(s_nk, last);
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + TQ;
-    const int n_all = S / TQ;
-    const int n_chunks = (p.mask != nullptr && *s_nk > 0) ? *s_nk : n_all;
+    // Variable-length batches: trailing key chunks whose additive mask is <= -1000 for EVERY key contribute exp2(..) == 0 exactly in
+    // fp32 (the running maximum comes from an attendable key), so they are skipped outright -- no load, no MMA, no softmax -- and the
+    // result is bit-identical to processing them (padding-skipping of FasterTransformer-style inference; also
+    // applies to training on LDDL's binned, partly padded batches).  The softmax warps scan the mask row while chunk 0 (always
+    // needed) is already being loaded and multiplied; every role picks the count up through nk_ready before it goes past chunk 0.
+    const bool scan = p.mask != nullptr && n_all > 1;
+    auto chunks_to_do = [&]() -> int {
+        if (!scan) return n_all;
+        mbar_wait(nk_ready, 0);
+        const int nk = *reinterpret_cast<volatile int*>(s_nk);
+        return nk > 0 ? nk : n_all;
+    };
 
     // Producer and MMA warps: warp-uniform loops (all lanes wait), tcgen05 / TMA instructions under elect_one() -- see gemm_sm100.cu.
     if (warp == FWD_WARP_TMA) {
@@ -135,9 +142,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdParam
         if (elect_one()) {
             mbar_expect_tx(q_full, TILE_BYTES);
             tma_load_3d(sQ, &tmap_qkv, q_full, h * HD, qt * TQ, b);
+            mbar_expect_tx(&k_full[0], TILE_BYTES);
+            tma_load_3d(sK, &tmap_qkv, &k_full[0], p.H + h * HD, 0, b);
+            mbar_expect_tx(&v_full[0], TILE_BYTES);
+            tma_load_3d(sV, &tmap_qkv, &v_full[0], 2 * p.H + h * HD, 0, b);
         }
         __syncwarp();
-        for (int j = 0; j < n_chunks; ++j) {
+        const int n_chunks = chunks_to_do();
+        for (int j = 1; j < n_chunks; ++j) {
             const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
             mbar_wait(&k_empty[st], ph ^ 1);
             if (elect_one()) {
@@ -154,32 +166,35 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdParam
         }
     } else if (warp == FWD_WARP_MMA) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t idesc_s = make_idesc_bf16(TQ, TQ, false, false);
+        constexpr uint32_t idesc_s = make_idesc_bf16(TQ, 64, false, false);
         constexpr uint32_t idesc_pv = make_idesc_bf16(TQ, HD, false, true);
         const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
-        auto issue_s = [&](int j_) {                       // S_j = Q K_j^T
+        auto issue_s = [&](int j_) {                       // S_j = Q K_j^T, one N = 64 group per key half
             const int st = j_ & 1;
             mbar_wait(&k_full[st], (j_ >> 1) & 1);
             tc_fence_after();
-            if (elect_one()) {
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                    umma_bf16_ss(tmem_S, make_smem_desc_sw128(aQ + kk * 32, 0, 1024),
-                                 make_smem_desc_sw128(aK + st * TILE_BYTES + kk * 32, 0, 1024), idesc_s, kk > 0 ? 1u : 0u);
-                umma_commit(&k_empty[st]);
-                umma_commit(s_full);
+            for (int hf = 0; hf < 2; ++hf) {
+                if (j_ >= 1) { mbar_wait(&s_free[hf], (j_ - 1) & 1); tc_fence_after(); }     // half hf of S_{j-1} is in registers
+                if (elect_one()) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        umma_bf16_ss(tmem_S + hf * 64, make_smem_desc_sw128(aQ + kk * 32, 0, 1024),
+                                     make_smem_desc_sw128(aK + st * TILE_BYTES + hf * HALF_BYTES + kk * 32, 0, 1024), idesc_s, kk > 0 ? 1u : 0u);
+                    umma_commit(&s_full[hf]);
+                    if (hf == 1) umma_commit(&k_empty[st]);
+                }
+                __syncwarp();
             }
-            __syncwarp();
         };
         mbar_wait(q_full, 0);
         issue_s(0);
+        const int n_chunks = chunks_to_do();
         for (int j = 0; j < n_chunks; ++j) {
             const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
-            // p_full(j): the softmax warps have read S_j completely and written P_j.  S_{j+1} goes FIRST (its columns are free), so the
-            // next chunk's softmax starts while PV_j executes.
-            mbar_wait(p_full, j & 1);
+            if (j + 1 < n_chunks) issue_s(j + 1);           // runs under chunk j's exponentials (its halves are released early)
+            mbar_wait(p_full, j & 1);                        // P_j written
             tc_fence_after();
-            if (j + 1 < n_chunks) issue_s(j + 1);
             mbar_wait(&v_full[st], ph);
             tc_fence_after();
             if (elect_one()) {
@@ -205,18 +220,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdParam
         float m_run = -INFINITY, l0 = 0.f;
         const unsigned long long drop_row = ((unsigned long long)(b * p.A + h) * S + (qt * TQ + r)) * (unsigned long long)S + hf * 64;
         const float* mrow = p.mask ? p.mask + (long long)b * S + hf * 64 : nullptr;
-        // which 128-key chunks carry a non-zero additive mask in MY half (warp-uniform bit set; typical batches: none or the tail)
+        // one pass over the mask row: which 128-key chunks carry a non-zero additive mask in MY half (warp-uniform bit set; typical
+        // batches: none or the tail) and which is the last chunk with an attendable key anywhere (all 8 warps cover the row together)
         uint32_t chunk_masked = 0;
         if (mrow) {
-            for (int j = 0; j < n_chunks; ++j) {
+            int last = 0;
+            for (int j = 0; j < n_all; ++j) {
                 const float2 m2 = __ldg(reinterpret_cast<const float2*>(mrow + j * TQ) + lane);
                 if (__any_sync(0xffffffffu, m2.x != 0.f || m2.y != 0.f)) chunk_masked |= 1u << j;
+                if (__any_sync(0xffffffffu, m2.x > -1000.0f || m2.y > -1000.0f)) last = j + 1;
+            }
+            if (scan) {
+                if (lane == 0) { if (last > 0) atomicMax(s_nk, last); __threadfence_block(); mbar_arrive(nk_ready); }
             }
         }
+        const int n_chunks = chunks_to_do();
         for (int j = 0; j < n_chunks; ++j) {
             const bool masked = (chunk_masked >> j) & 1u;
             const float* mk = mrow + j * TQ;
-            mbar_wait(s_full, j & 1);
+            mbar_wait(&s_full[hf], j & 1);
             tc_fence_after();
             uint32_t v[32];
             // ---- pass 1: maximum of my 64 columns
@@ -271,6 +293,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdParam
             for (int pc = 0; pc < 2; ++pc) {
                 tmem_ld32(tS + pc * 32, v);
                 tmem_ld_wait();
+                if (pc == 1) {                                         // my half of S_j is in registers: its columns may take S_{j+1}
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s_free[hf]);
+                }
                 float e[32];
                 if (masked) {
 #pragma unroll
@@ -308,7 +335,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdParam
             const float rs = rs0 + rs1;
             l0 = l0 * alpha + rs;
             m_run = m_new;
-            tc_fence_before();
+            tc_fence_before();                                         // orders the O rescale (tcgen05.st) before PV_j
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full);                       // one arrival per warp (count = 8)
@@ -360,7 +387,6 @@ constexpr int BWD_THREADS = 576;       // warps 0..15: compute, 16: TMA + TMEM a
 constexpr int BWD_COMPUTE_WARPS = 16;
 constexpr int BWD_WARP_TMA = 16, BWD_WARP_MMA = 17;
 constexpr int BWD_GROUP_WARPS = 8;
-constexpr int HALF_BYTES = 64 * HD * 2;    // 8 KB: 64 key rows of a K / V tile
 
 struct AttnBwdParams {
     const float* mask; const float* lse; const float* delta;
@@ -426,8 +452,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     uint64_t* pair_done = bars + 17;  // dK(t), dQ(t) retired: sdS may be rewritten
     uint64_t* dkv_full = bars + 18;   // kv tile finished: dK, dV (and at the end dQ) complete
     uint64_t* dkv_read = bars + 19;   // accumulators drained (16)
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
-    int* s_nk = reinterpret_cast<int*>(bars + 20) + 1;      // kv tiles that hold at least one attendable key
+    uint64_t* nk_ready = bars + 20;   // number of kv tiles to process is known (16 compute-warp arrivals)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 21);
+    int* s_nk = reinterpret_cast<int*>(bars + 21) + 1;      // kv tiles that hold at least one attendable key
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = blockIdx.x, b = blockIdx.y;
@@ -443,24 +470,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         }
         mbar_init(p_full, BWD_COMPUTE_WARPS); mbar_init(ds_full, BWD_COMPUTE_WARPS);
         mbar_init(dv_done, 1); mbar_init(pair_done, 1); mbar_init(dkv_full, 1); mbar_init(dkv_read, BWD_COMPUTE_WARPS);
+        mbar_init(nk_ready, BWD_COMPUTE_WARPS);
         fence_barrier_init();
         *s_nk = 0;
     }
     if (warp == BWD_WARP_TMA) { tmem_alloc(tmem_ptr, 512); tmem_relinquish(); }
-    // trailing kv tiles that are masked out for every key (additive mask <= -1000) have P == 0 exactly: dK = dV = 0 there and dQ gets
-    // nothing from them, so they are skipped and their dK / dV rows are written as zeros (bit-identical to computing them)
-    if (p.mask != nullptr) {
-        __syncthreads();
-        int last = 0;
-        for (int k = threadIdx.x; k < S; k += BWD_THREADS)
-            if (__ldg(p.mask + (long long)b * S + k) > -1000.0f) last = k / TQ + 1;
-        last = __reduce_max_sync(0xffffffffu, last);
-        if (lane == 0 && last > 0) atomicMax(s_nk, last);
-    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const int nk = (p.mask != nullptr && *s_nk > 0) ? *s_nk : n;
+    // trailing kv tiles that are masked out for every key (additive mask <= -1000) have P == 0 exactly: dK = dV = 0 there and dQ gets
+    // nothing from them, so they are skipped and their dK / dV rows are written as zeros (bit-identical to computing them).  The compute
+    // warps find the count while they stage the mask row; the producer / MMA warps pick it up (nk_ready) before they go past kv tile 0.
+    const bool scan = p.mask != nullptr && n > 1;
+    auto tiles_to_do = [&]() -> int {
+        if (!scan) return n;
+        mbar_wait(nk_ready, 0);
+        const int v_ = *reinterpret_cast<volatile int*>(s_nk);
+        return v_ > 0 ? v_ : n;
+    };
     const uint32_t tmem_base = *tmem_ptr;
     const uint32_t tmem_dQ = tmem_base, tmem_dK = tmem_base + 256, tmem_dV = tmem_base + 320, tmem_S = tmem_base + 384, tmem_dP = tmem_base + 448;
 
@@ -478,6 +505,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             }
         }
         __syncwarp();
+        const int nk = tiles_to_do();
         for (int j = 1; j < nk; ++j) {
             mbar_wait(kv_empty, (j - 1) & 1);                // every MMA that reads K_{j-1} / V_{j-1} has retired
             if (elect_one()) {
@@ -540,7 +568,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             __syncwarp();
         };
         auto wait = [&](uint64_t* bar, int phase) { mbar_wait(bar, (uint32_t)phase & 1u); tc_fence_after(); };
+        int nk = n;
         for (int j = 0; j < nk; ++j) {
+            if (j == 1) nk = tiles_to_do();                  // known long before kv tile 0 is finished
+            if (j >= nk) break;
             wait(kv_full, j);
             if (j >= 1) wait(dkv_read, j - 1);              // dK / dV accumulators of the previous kv tile drained
             for (int i = 0; i < n; ++i) {
@@ -574,8 +605,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         const int r = q4 * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
         const int ct = threadIdx.x;
-        for (int i = ct; i < S; i += BWD_COMPUTE_WARPS * 32) sMask[i] = p.mask ? p.mask[(long long)b * S + i] * LOG2E : 0.f;
+        {
+            int last = 0;
+            for (int i = ct; i < S; i += BWD_COMPUTE_WARPS * 32) {
+                const float mv = p.mask ? p.mask[(long long)b * S + i] : 0.f;
+                sMask[i] = mv * LOG2E;
+                if (mv > -1000.0f) last = i / TQ + 1;
+            }
+            if (scan) {
+                last = __reduce_max_sync(0xffffffffu, last);
+                if (lane == 0) { if (last > 0) atomicMax(s_nk, last); __threadfence_block(); mbar_arrive(nk_ready); }
+            }
+        }
         named_bar_sync(1, BWD_COMPUTE_WARPS * 32);
+        const int nk = tiles_to_do();
         const long long bh = (long long)b * p.A + h;
         const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS);
         const unsigned long long seed = effective_seed(p.seed, p.seed_dev);

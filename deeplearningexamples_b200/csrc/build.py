@@ -78,5 +78,5 @@ def build(force=False, verbose=False):
 
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose=True)
-    if "--variant-nohint" in sys.argv:
-        print("built", build_variant("nohint", ["-DDLE_MBAR_HINT_NS=0"]))
+    if "--variant-hint" in sys.argv:
+        print("built", build_variant("hint", ["-DDLE_MBAR_HINT_NS=0x989680"]))

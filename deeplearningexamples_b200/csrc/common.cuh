@@ -266,8 +266,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // for issue slots with the softmax warps of the same SM sub-partition.
 // Watchdog: a wait that has not completed after 4 s of wall clock (kernels here last milliseconds) is a protocol bug; trap so the
 // launch fails with an error instead of hanging the GPU.
+// Suspend-time hint of mbarrier.try_wait: 0 = none (the hardware's default time limit per attempt), else nanoseconds.  Round 1 used
+// 10 ms to park single-lane waiters; since the producer / MMA warps wait warp-wide (see gemm_sm100.cu) the un-hinted form measures
+// 0.6 % faster on the whole step and 3 % on attention backward (profiles/README.md, same-box A/B), so it is the default.
 #ifndef DLE_MBAR_HINT_NS
-#define DLE_MBAR_HINT_NS 0x989680          /* 10 ms; 0 = no suspend-time hint (hardware default time limit per try_wait) */
+#define DLE_MBAR_HINT_NS 0
 #endif
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t addr, uint32_t parity) {
     uint32_t ok;

@@ -220,14 +220,30 @@ add_ln_fwd2_kernel(const bf16* __restrict__ x, const bf16* __restrict__ bias, co
         bs[j] = bias ? *reinterpret_cast<const uint4*>(bias + col) : make_uint4(0u, 0u, 0u, 0u);
     }
     int par = 0;
-    for (long long row = (long long)blockIdx.x * LN2_ROWS + rg; row < T; row += (long long)gridDim.x * LN2_ROWS, par ^= 1) {
+    // software prefetch: the loads of the NEXT row are issued before this row's reductions and barriers, so two rows per warp pair are
+    // in flight (round 1 measured 2.6 TB/s with one: 16 resident warps x 32 B per lane do not cover the HBM latency-bandwidth product)
+    const long long stride = (long long)gridDim.x * LN2_ROWS;
+    long long row = (long long)blockIdx.x * LN2_ROWS + rg;
+    uint4 nxt[J2];
+    if (row < T) {
+#pragma unroll
+        for (int j = 0; j < J2; ++j) nxt[j] = ld_global_nc_v4(x + row * H + j * 512 + t64 * 8);
+    }
+    for (; row < T; row += stride, par ^= 1) {
         float z[J2 * 8];
         float s = 0.f;
+        uint4 cur[J2];
+#pragma unroll
+        for (int j = 0; j < J2; ++j) cur[j] = nxt[j];
+        if (row + stride < T) {
+#pragma unroll
+            for (int j = 0; j < J2; ++j) nxt[j] = ld_global_nc_v4(x + (row + stride) * H + j * 512 + t64 * 8);
+        }
 #pragma unroll
         for (int j = 0; j < J2; ++j) {
             const int col = j * 512 + t64 * 8;
             float b[8];
-            unpack8(ld_global_nc_v4(x + row * H + col), z + j * 8);
+            unpack8(cur[j], z + j * 8);
             unpack8(bs[j], b);
 #pragma unroll
             for (int i = 0; i < 8; ++i) z[j * 8 + i] += b[i];
@@ -274,7 +290,7 @@ add_ln_fwd2_kernel(const bf16* __restrict__ x, const bf16* __restrict__ bias, co
 }
 
 template <int J2>
-__global__ void __launch_bounds__(LN2_THREADS)
+__global__ void __launch_bounds__(LN2_THREADS, J2 == 1 ? 4 : 2)
 add_ln_bwd2_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, const float* __restrict__ mean_in,
                    const float* __restrict__ rstd_in, const bf16* __restrict__ gamma, bf16* __restrict__ dz_out,
                    bf16* __restrict__ dx_out, float* __restrict__ part_dgamma, float* __restrict__ part_dbeta,
@@ -293,16 +309,40 @@ add_ln_bwd2_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, cons
     for (int i = 0; i < J2 * 8; ++i) { ag[i] = 0.f; ab[i] = 0.f; ax[i] = 0.f; }
     const float invH = 1.0f / (float)H;
     int par = 0;
-    for (long long row = (long long)blockIdx.x * LN2_ROWS + rg; row < T; row += (long long)gridDim.x * LN2_ROWS, par ^= 1) {
-        const float mean = mean_in[row], rstd = rstd_in[row];
+    // software prefetch of the next row (see add_ln_fwd2_kernel): two rows of dy and z per warp pair in flight
+    const long long stride = (long long)gridDim.x * LN2_ROWS;
+    long long row = (long long)blockIdx.x * LN2_ROWS + rg;
+    uint4 ndy[J2], nz[J2];
+    float nmean = 0.f, nrstd = 0.f;
+    if (row < T) {
+#pragma unroll
+        for (int j = 0; j < J2; ++j) {
+            ndy[j] = ld_global_nc_v4(dy + row * H + j * 512 + t64 * 8);
+            nz[j] = ld_global_nc_v4(z + row * H + j * 512 + t64 * 8);
+        }
+        nmean = mean_in[row]; nrstd = rstd_in[row];
+    }
+    for (; row < T; row += stride, par ^= 1) {
+        const float mean = nmean, rstd = nrstd;
+        uint4 cdy[J2], cz[J2];
+#pragma unroll
+        for (int j = 0; j < J2; ++j) { cdy[j] = ndy[j]; cz[j] = nz[j]; }
+        if (row + stride < T) {
+#pragma unroll
+            for (int j = 0; j < J2; ++j) {
+                ndy[j] = ld_global_nc_v4(dy + (row + stride) * H + j * 512 + t64 * 8);
+                nz[j] = ld_global_nc_v4(z + (row + stride) * H + j * 512 + t64 * 8);
+            }
+            nmean = mean_in[row + stride]; nrstd = rstd_in[row + stride];
+        }
         float g[J2 * 8], xh[J2 * 8];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int j = 0; j < J2; ++j) {
             const int col = j * 512 + t64 * 8;
             float d[8], zz[8], gg[8];
-            unpack8(ld_global_nc_v4(dy + row * H + col), d);
-            unpack8(ld_global_nc_v4(z + row * H + col), zz);
+            unpack8(cdy[j], d);
+            unpack8(cz[j], zz);
             unpack8(gm[j], gg);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
