@@ -29,7 +29,10 @@ def _need_ref():
         pytest.skip("baseline/_ref/BERT not installed (python baseline/install_ref.py where /root/reference exists)")
 
 
-def _run(arm, out, extra, max_steps, tmp_path, timeout=600):
+def _run(arm, out, extra, steps, tmp_path, timeout=600):
+    """`steps` optimizer steps of a 100-step schedule (--steps_this_run): the reference's --cuda_graphs warm-up trains 11 extra steps
+    before the first counted one (run_pretraining.py:611-616), which a schedule as short as the run itself would push past its end
+    (poly decay of a negative base = NaN learning rate, in the reference as well)."""
     cfg = tmp_path / "small.json"
     cfg.write_text(json.dumps(SMALL))
     with socket.socket() as s:
@@ -38,7 +41,7 @@ def _run(arm, out, extra, max_steps, tmp_path, timeout=600):
     env = dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     cmd = [sys.executable, os.path.join(ROOT, "tools", "run_reference_driver.py"), "--arm", arm, "--",
            "--input_dir", "synthetic?seq_len=128&max_pred=20&samples=512&bin_size=0", "--config_file", str(cfg), "--output_dir", str(out), "--vocab_file", "vocab.txt",
-           "--train_batch_size", "8", "--max_seq_length", "128", "--max_predictions_per_seq", "20", "--max_steps", str(max_steps),
+           "--train_batch_size", "8", "--max_seq_length", "128", "--max_predictions_per_seq", "20", "--max_steps", "100", "--steps_this_run", str(steps),
            "--warmup_proportion", "0.1", "--learning_rate", "1e-3", "--seed", "42", "--do_train", "--fp16", "--allreduce_post_accumulation",
            "--allreduce_post_accumulation_fp16", "--disable_jit_fusions", "--num_steps_per_checkpoint", "5", "--log_freq", "1",
            "--json-summary", str(out / "dllogger.json"), "--disable_progress_bar"] + extra
