@@ -266,7 +266,7 @@ def run_ours(args):
             os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
         # record what NCCL sets up (algorithms, channels, NVLS) without touching stdout: rank 0 writes its INIT log to a file
         nccl_log = None
-        if rank == 0 and "NCCL_DEBUG" not in os.environ:
+        if rank == 0 and os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):
             nccl_log = f"/tmp/dle_nccl_init_{os.getpid()}.log"
             os.environ.update(NCCL_DEBUG="INFO", NCCL_DEBUG_SUBSYS="INIT,ENV,TUNING", NCCL_DEBUG_FILE=nccl_log)
         dist.init_process_group(backend="nccl", init_method="env://", device_id=device)

@@ -198,6 +198,7 @@ add_ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, const
 // ---------------------------------------------------------------------------------------------
 constexpr int LN2_ROWS = 4;                       // row groups per CTA
 constexpr int LN2_THREADS = LN2_ROWS * 64;
+constexpr int LN2_DEPTH = 3;                      // rows per warp pair in flight (cp.async prefetch ring)
 
 __device__ __forceinline__ void pair_bar(int rg) { asm volatile("bar.sync %0, 64;" ::"r"(rg + 1) : "memory"); }
 
@@ -220,25 +221,32 @@ add_ln_fwd2_kernel(const bf16* __restrict__ x, const bf16* __restrict__ bias, co
         bs[j] = bias ? *reinterpret_cast<const uint4*>(bias + col) : make_uint4(0u, 0u, 0u, 0u);
     }
     int par = 0;
-    // software prefetch: the loads of the NEXT row are issued before this row's reductions and barriers, so two rows per warp pair are
-    // in flight (round 1 measured 2.6 TB/s with one: 16 resident warps x 32 B per lane do not cover the HBM latency-bandwidth product)
+    // Prefetch ring: every thread copies ITS OWN 16-byte pieces of the next LN2_DEPTH rows into a private shared-memory slot with
+    // cp.async (no registers, no barrier: a thread only ever reads back what it copied), so LN2_DEPTH rows per warp pair are in
+    // flight.  Round 1 had one row in flight (2.6 TB/s: 16 resident warps x 32 B per lane do not cover HBM's latency-bandwidth
+    // product), a register double buffer reached 4.5 TB/s.
+    __shared__ uint4 ring[LN2_DEPTH][J2][LN2_THREADS];
     const long long stride = (long long)gridDim.x * LN2_ROWS;
     long long row = (long long)blockIdx.x * LN2_ROWS + rg;
-    uint4 nxt[J2];
-    if (row < T) {
+    auto prefetch = [&](int slot, long long r_) {
+        if (r_ < T) {
 #pragma unroll
-        for (int j = 0; j < J2; ++j) nxt[j] = ld_global_nc_v4(x + row * H + j * 512 + t64 * 8);
-    }
+            for (int j = 0; j < J2; ++j) cp_async16(smem_u32(&ring[slot][j][threadIdx.x]), x + r_ * H + j * 512 + t64 * 8);
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int d = 0; d < LN2_DEPTH; ++d) prefetch(d, row + d * stride);
+    int slot = 0;
     for (; row < T; row += stride, par ^= 1) {
         float z[J2 * 8];
         float s = 0.f;
         uint4 cur[J2];
+        cp_async_wait<LN2_DEPTH - 1>();
 #pragma unroll
-        for (int j = 0; j < J2; ++j) cur[j] = nxt[j];
-        if (row + stride < T) {
-#pragma unroll
-            for (int j = 0; j < J2; ++j) nxt[j] = ld_global_nc_v4(x + (row + stride) * H + j * 512 + t64 * 8);
-        }
+        for (int j = 0; j < J2; ++j) cur[j] = lds_u4(smem_u32(&ring[slot][j][threadIdx.x]));
+        prefetch(slot, row + LN2_DEPTH * stride);
+        slot = (slot + 1 == LN2_DEPTH) ? 0 : slot + 1;
 #pragma unroll
         for (int j = 0; j < J2; ++j) {
             const int col = j * 512 + t64 * 8;
@@ -299,7 +307,8 @@ add_ln_bwd2_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, cons
     seed = effective_seed(seed, seed_dev);
     constexpr int H = J2 * 512;
     __shared__ float ex[2][LN2_ROWS][2][2];
-    __shared__ float red[LN2_ROWS][H];
+    extern __shared__ __align__(16) uint8_t ln_smem[];          // max(prefetch ring, column-reduction buffer)
+    float (*red)[H] = reinterpret_cast<float (*)[H]>(ln_smem);
     const int t64 = threadIdx.x & 63, rg = threadIdx.x >> 6, wp = (threadIdx.x >> 5) & 1, lane = threadIdx.x & 31;
     uint4 gm[J2];
     float ag[J2 * 8], ab[J2 * 8], ax[J2 * 8];
@@ -309,37 +318,42 @@ add_ln_bwd2_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, cons
     for (int i = 0; i < J2 * 8; ++i) { ag[i] = 0.f; ab[i] = 0.f; ax[i] = 0.f; }
     const float invH = 1.0f / (float)H;
     int par = 0;
-    // software prefetch of the next row (see add_ln_fwd2_kernel): two rows of dy and z per warp pair in flight
+    // cp.async prefetch ring (see add_ln_fwd2_kernel): LN2_DEPTH rows of dy and z per warp pair in flight, no staging registers.  The
+    // ring aliases the column-reduction buffer `red`, which is only used after the row loop.
+    uint4 (*ring)[2 * J2][LN2_THREADS] = reinterpret_cast<uint4 (*)[2 * J2][LN2_THREADS]>(ln_smem);
     const long long stride = (long long)gridDim.x * LN2_ROWS;
     long long row = (long long)blockIdx.x * LN2_ROWS + rg;
-    uint4 ndy[J2], nz[J2];
-    float nmean = 0.f, nrstd = 0.f;
-    if (row < T) {
+    auto prefetch = [&](int slot, long long r_) {
+        if (r_ < T) {
 #pragma unroll
-        for (int j = 0; j < J2; ++j) {
-            ndy[j] = ld_global_nc_v4(dy + row * H + j * 512 + t64 * 8);
-            nz[j] = ld_global_nc_v4(z + row * H + j * 512 + t64 * 8);
+            for (int j = 0; j < J2; ++j) {
+                cp_async16(smem_u32(&ring[slot][j][threadIdx.x]), dy + r_ * H + j * 512 + t64 * 8);
+                cp_async16(smem_u32(&ring[slot][J2 + j][threadIdx.x]), z + r_ * H + j * 512 + t64 * 8);
+            }
         }
-        nmean = mean_in[row]; nrstd = rstd_in[row];
-    }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int d = 0; d < LN2_DEPTH; ++d) prefetch(d, row + d * stride);
+    float nmean = 0.f, nrstd = 0.f;
+    if (row < T) { nmean = mean_in[row]; nrstd = rstd_in[row]; }
+    int slot = 0;
     for (; row < T; row += stride, par ^= 1) {
         const float mean = nmean, rstd = nrstd;
         uint4 cdy[J2], cz[J2];
+        cp_async_wait<LN2_DEPTH - 1>();
 #pragma unroll
-        for (int j = 0; j < J2; ++j) { cdy[j] = ndy[j]; cz[j] = nz[j]; }
-        if (row + stride < T) {
-#pragma unroll
-            for (int j = 0; j < J2; ++j) {
-                ndy[j] = ld_global_nc_v4(dy + (row + stride) * H + j * 512 + t64 * 8);
-                nz[j] = ld_global_nc_v4(z + (row + stride) * H + j * 512 + t64 * 8);
-            }
-            nmean = mean_in[row + stride]; nrstd = rstd_in[row + stride];
+        for (int j = 0; j < J2; ++j) {
+            cdy[j] = lds_u4(smem_u32(&ring[slot][j][threadIdx.x]));
+            cz[j] = lds_u4(smem_u32(&ring[slot][J2 + j][threadIdx.x]));
         }
+        prefetch(slot, row + LN2_DEPTH * stride);
+        slot = (slot + 1 == LN2_DEPTH) ? 0 : slot + 1;
+        if (row + stride < T) { nmean = mean_in[row + stride]; nrstd = rstd_in[row + stride]; }
         float g[J2 * 8], xh[J2 * 8];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int j = 0; j < J2; ++j) {
-            const int col = j * 512 + t64 * 8;
             float d[8], zz[8], gg[8];
             unpack8(cdy[j], d);
             unpack8(cz[j], zz);
@@ -377,6 +391,7 @@ add_ln_bwd2_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, cons
             for (int i = 0; i < 8; ++i) ax[j * 8 + i] += round_bf16(dzv[i]);
         }
     }
+    cp_async_wait<0>();
     float* outs[3] = {part_dgamma, part_dbeta, part_dbias};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -397,6 +412,20 @@ add_ln_bwd2_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ z, cons
 }
 // DLE_LN_ONE_WARP=1 selects the one-warp-per-row kernels (A/B measurements)
 static bool ln_force_one_warp() { const char* e = getenv("DLE_LN_ONE_WARP"); return e && e[0] == '1'; }
+static int ln2_bwd_smem(int j2) {                 // bytes: the larger of the prefetch ring and the [LN2_ROWS][H] fp32 reduction buffer
+    const int ring = LN2_DEPTH * 2 * j2 * LN2_THREADS * 16, red = LN2_ROWS * j2 * 512 * 4;
+    return ring > red ? ring : red;
+}
+template <int J2> static int ln2_bwd_attr() {       // > 48 KB of shared memory per CTA needs the opt-in attribute (per device)
+    static bool done[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return DLE_ERR_CUDA;
+    if (!done[dev]) {
+        if (cudaFuncSetAttribute(add_ln_bwd2_kernel<J2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ln2_bwd_smem(J2)) != cudaSuccess) return DLE_ERR_CUDA;
+        done[dev] = true;
+    }
+    return DLE_OK;
+}
 static int ln2_grid(long long T) {
     long long g = (T + LN2_ROWS - 1) / LN2_ROWS, cap = (long long)sm_count() * 4;
     return (int)(g < cap ? (g > 0 ? g : 1) : cap);
@@ -743,8 +772,9 @@ extern "C" int dle_add_ln_bwd(const void* dy, const void* z, const float* mean, 
     const uint32_t th = dropout_p > 0.f ? dropout_thresh16(dropout_p) : 0u;
     const float sc = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
     if (H % 512 == 0 && !ln_force_one_warp()) {
-        if (H == 1024) add_ln_bwd2_kernel<2><<<ln2_grid(T), LN2_THREADS, 0, S_(stream)>>>(B_(dy), B_(z), mean, rstd, B_(gamma), BM_(dz_out), BM_(dx_out), part_dgamma, part_dbeta, part_dbias, T, th, sc, seed, reinterpret_cast<const unsigned long long*>(seed_dev), dropout_stream);
-        else add_ln_bwd2_kernel<1><<<ln2_grid(T), LN2_THREADS, 0, S_(stream)>>>(B_(dy), B_(z), mean, rstd, B_(gamma), BM_(dz_out), BM_(dx_out), part_dgamma, part_dbeta, part_dbias, T, th, sc, seed, reinterpret_cast<const unsigned long long*>(seed_dev), dropout_stream);
+        if (int rc = (H == 1024 ? ln2_bwd_attr<2>() : ln2_bwd_attr<1>())) return rc;
+        if (H == 1024) add_ln_bwd2_kernel<2><<<ln2_grid(T), LN2_THREADS, ln2_bwd_smem(2), S_(stream)>>>(B_(dy), B_(z), mean, rstd, B_(gamma), BM_(dz_out), BM_(dx_out), part_dgamma, part_dbeta, part_dbias, T, th, sc, seed, reinterpret_cast<const unsigned long long*>(seed_dev), dropout_stream);
+        else add_ln_bwd2_kernel<1><<<ln2_grid(T), LN2_THREADS, ln2_bwd_smem(1), S_(stream)>>>(B_(dy), B_(z), mean, rstd, B_(gamma), BM_(dz_out), BM_(dx_out), part_dgamma, part_dbeta, part_dbias, T, th, sc, seed, reinterpret_cast<const unsigned long long*>(seed_dev), dropout_stream);
         DLE_LAUNCH_CHECK();
         return DLE_OK;
     }

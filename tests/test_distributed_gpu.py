@@ -98,5 +98,11 @@ def test_two_rank_ddp_step_equals_one_rank_step_on_concatenated_batch(tmp_path, 
         m2, v2 = two["state"][k]
         m1, v1 = state[k]
         assert rel(m2, m1) < max(tol, 2e-5) and rel(v2, v1) < max(2 * tol, 4e-5), ("moments", k, rel(m2, m1), rel(v2, v1))
-        # parameters: compare the UPDATE (new - initial would need the initial copy; masters are within the step size of each other)
-        assert rel(two["masters"][k], masters[k]) < tol * 1e-1 + 1e-6, ("param", k, rel(two["masters"][k], masters[k]))
+        # parameters.  fp32: identical up to summation order.  bf16: the first LAMB step is sign-like (m^ / sqrt(v^) = g / |g|), so a
+        # gradient entry that rounds to opposite signs on the two paths moves that element by up to 2 * lr * trust-ratio; zero-initialised
+        # parameters (biases) consist of nothing but this update, hence an absolute bound of two step sizes next to the relative one
+        diff = (two["masters"][k].float().cpu() - masters[k].float().cpu()).abs().max().item()
+        if dtype_name == "float32":
+            assert rel(two["masters"][k], masters[k]) < 1e-5, ("param", k, rel(two["masters"][k], masters[k]))
+        else:
+            assert diff <= 2.2e-3 * max(1.0, masters[k].float().abs().max().item()), ("param", k, diff)
