@@ -406,12 +406,16 @@ def run_ours(args):
     e2e = T.global_throughput(B, n, args.steps, ms_e2e)
     pk = peaks()
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    tensor_active = None
+    tpath = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
     if os.path.exists(tpath):                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
         tj = json.load(open(tpath))
         traffic, traffic_src = tj["avg_dram_traffic_bytes_per_launch"], (
-            "profiles/r01_gemm_traffic.json (ncu --set full, 12 forward GEMM launches of this command; the same 12 launches move "
+            "profiles/r02_gemm_traffic.json (ncu --set full, 12 forward GEMM launches of this command; the same 12 launches move "
             f"{tj.get('avg_algorithmic_bytes_per_launch', 0)} algorithmic bytes on average -- algorithmic_bytes_per_launch_avg below averages ALL timed launches)")
+        ls_ = tj.get("launches", [])
+        if ls_:                                   # time-weighted sm__pipe_tensor_cycles_active of the same 12 launches (ncu, not live)
+            tensor_active = round(sum(l["tensor_active_pct"] * l["time_us"] for l in ls_) / sum(l["time_us"] for l in ls_), 1)
     by_shape = {}
     for a_, b_, f_, tag in prof:
         d = by_shape.setdefault(tag, [0, 0.0, 0.0])
@@ -435,7 +439,7 @@ def run_ours(args):
             "roofline": {"kernel": "gemm_bf16_tcgen05_kernel (all dense projections/FFN, fwd+dgrad+wgrad)", "bound": "tensor",
                          "achieved": round(ach, 1), "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": round(ach / pk["tf_sustained"], 4),
                          "peak_source": pk["source"] + " (bf16_tflops_sustained: kernel timed inside a long step)",
-                         "traffic": traffic, "traffic_source": traffic_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "tensor_pipe_active_pct_ncu": tensor_active,
                          "algorithmic_bytes_per_launch_avg": int(sum(2.0 * (m * k + n * k + m * n) for _, _, _, (m, n, k, *_r) in prof) / max(len(prof), 1)),
                          "launches_timed": len(prof), "share_of_step": round((gemm_ms / prof_steps) / (ms_e2e / args.steps), 4),
                          "by_shape_top": gemm_table[:12],

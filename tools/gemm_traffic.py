@@ -13,7 +13,7 @@ UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us":
 
 
 def main(raw, out, tokens, source):
-    rows = list(csv.reader(l for l in open(raw, newline="") if not l.startswith("==")))
+    rows = list(csv.reader(l for l in open(raw, newline="") if l.strip() and not l.startswith("==")))
     hdr, units, body = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(hdr)}
 
