@@ -383,9 +383,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdParam
 //   MMA order per pair : S(t,0) dP(t,0) S(t,1) dV(t-1) dP(t,1) dK(t-1) dQ(t-1) -- the accumulating MMAs trail by one pair, so the issuer
 //           never blocks the next pair's S / dP behind operands (P~, dS) that the compute warps are still writing.
 // =================================================================================================
-constexpr int BWD_THREADS = 576;       // warps 0..15: compute, 16: TMA + TMEM alloc, 17: MMA issuer (highest ids: favoured by the arbiter)
+// Two MMA-issuing warps.  The hand-off trace (tools/attn_trace.py) shows one in-order issuer spending ~3100 of
+// the ~5500 clk pair period inside tcgen05.mma issue (~80 clk per 128x64x16 instruction) and the accumulating MMAs of pair t-1 reaching
+// the tensor pipe ~4000 clk after their operands were ready, because they queue behind S / dP issues that wait on the compute warps.
+// Warp 17 therefore issues only S / dP, warp 18 only dV / dK / dQ: each follows its own operands (measured 911 -> 857 us at B=128).
+constexpr int BWD_THREADS = 608;       // warps 0..15: compute, 16: TMA + TMEM alloc, 17: S/dP issuer, 18: dV/dK/dQ issuer
 constexpr int BWD_COMPUTE_WARPS = 16;
-constexpr int BWD_WARP_TMA = 16, BWD_WARP_MMA = 17;
+constexpr int BWD_WARP_TMA = 16, BWD_WARP_MMA = 17, BWD_WARP_MMA2 = 18;
 constexpr int BWD_GROUP_WARPS = 8;
 
 struct AttnBwdParams {
@@ -427,6 +431,21 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ dctx, const bf16* __r
     delta[((long long)b * A + h) * S + s] = acc;
 }
 
+// Measurement-only build switch (-DDLE_ATTN_TRACE, csrc/build.py --variant-trace): lane 0 of the MMA warp and of one compute warp per group
+// of ONE CTA stamps clock64() at every barrier hand-off into a __device__ buffer, and every CTA records its SM and start / end
+// %globaltimer.  tools/attn_trace.py turns that into the per-pair timeline DESIGN.md section 8 discusses.  Not compiled into the product.
+#ifdef DLE_ATTN_TRACE
+constexpr int TRACE_CAP = 4096, TRACE_CTA = 709, TRACE_MAX_CTAS = 8192;
+__device__ unsigned long long g_attn_trace[4][TRACE_CAP];
+__device__ int g_attn_trace_n[4];
+__device__ unsigned long long g_attn_cta[TRACE_MAX_CTAS][3];
+#define TR(code, t) do { if (tr_slot >= 0 && lane == 0 && tr_n < TRACE_CAP) g_attn_trace[tr_slot][tr_n++] = ((unsigned long long)clock64() << 16) | ((unsigned long long)(code) << 8) | (unsigned long long)((t) & 255); } while (0)
+#define TR_END() do { if (tr_slot >= 0 && lane == 0) g_attn_trace_n[tr_slot] = tr_n; } while (0)
+#else
+#define TR(code, t) do {} while (0)
+#define TR_END() do {} while (0)
+#endif
+
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do, const AttnBwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -458,6 +477,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = blockIdx.x, b = blockIdx.y;
+#ifdef DLE_ATTN_TRACE
+    const int cta_lin = blockIdx.y * gridDim.x + blockIdx.x;
+    const int tr_slot = (cta_lin != TRACE_CTA) ? -1 : (warp == BWD_WARP_MMA ? 0 : warp == 0 ? 1 : warp == 8 ? 2 : warp == BWD_WARP_MMA2 ? 3 : -1);
+    int tr_n = 0;
+    if (threadIdx.x == 0 && cta_lin < TRACE_MAX_CTAS) {
+        unsigned int smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_attn_cta[cta_lin][0] = smid; g_attn_cta[cta_lin][1] = global_timer_ns();
+    }
+    TR(1, 0);
+#endif
 
     if (threadIdx.x == 0) {
         if ((smem_u32(smem) & 1023u) != 0) __trap();          // SWIZZLE_128B tiles need a 1024-byte aligned base
@@ -515,8 +544,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             }
             __syncwarp();
         }
-    } else if (warp == BWD_WARP_MMA) {
-        // ===================== MMA issuer =====================
+    } else if (warp == BWD_WARP_MMA || warp == BWD_WARP_MMA2) {
+        // ===================== MMA issuer(s) =====================
         constexpr uint32_t id_h = make_idesc_bf16(TQ, 64, false, false);      // S half, dP half: [128 q] x [64 keys], K = d
         constexpr uint32_t id_mm = make_idesc_bf16(TQ, HD, true, true);       // dV, dK
         constexpr uint32_t id_km = make_idesc_bf16(TQ, HD, false, true);      // dQ
@@ -569,34 +598,52 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         };
         auto wait = [&](uint64_t* bar, int phase) { mbar_wait(bar, (uint32_t)phase & 1u); tc_fence_after(); };
         int nk = n;
-        for (int j = 0; j < nk; ++j) {
-            if (j == 1) nk = tiles_to_do();                  // known long before kv tile 0 is finished
-            if (j >= nk) break;
-            wait(kv_full, j);
-            if (j >= 1) wait(dkv_read, j - 1);              // dK / dV accumulators of the previous kv tile drained
-            for (int i = 0; i < n; ++i) {
-                const int t = j * n + i;
-                if (j == 0) wait(&q_full[i], 0);
-                if (t >= 1) wait(&s_free[1], t - 1);        // group 1 has S(t-1, 1) in registers: the S columns are free
-                issue_s(i, 0);
-                if (t >= 1) wait(&dp_free[1], t - 1);
-                issue_dp(i, 0);
-                wait(&s_free[0], t);
-                issue_s(i, 1);
-                if (i >= 1) { wait(p_full, t - 1); issue_dv(i - 1); }
-                wait(&dp_free[0], t);
-                issue_dp(i, 1);
-                if (i >= 1) { wait(ds_full, t - 1); issue_dkdq(i - 1, j); }
+        if (warp == BWD_WARP_MMA) {
+            // ---- S / dP issuer: paced only by the compute warps taking the previous halves out of TMEM
+            for (int j = 0; j < nk; ++j) {
+                if (j == 1) nk = tiles_to_do();
+                if (j >= nk) break;
+                wait(kv_full, j); TR(10, j);
+                for (int i = 0; i < n; ++i) {
+                    const int t = j * n + i;
+                    if (j == 0) { wait(&q_full[i], 0); TR(12, t); }
+                    if (t >= 1) wait(&s_free[1], t - 1);
+                    TR(13, t);
+                    issue_s(i, 0); TR(14, t);
+                    if (t >= 1) wait(&dp_free[1], t - 1);
+                    TR(15, t);
+                    issue_dp(i, 0); TR(16, t);
+                    wait(&s_free[0], t); TR(17, t);
+                    issue_s(i, 1); TR(18, t);
+                    wait(&dp_free[0], t); TR(21, t);
+                    issue_dp(i, 1); TR(22, t);
+                }
             }
-            const int tl = j * n + n - 1;                   // the trailing pair of this kv tile
-            wait(p_full, tl); issue_dv(n - 1);
-            wait(ds_full, tl); issue_dkdq(n - 1, j);
-            if (elect_one()) {
-                umma_commit(kv_empty);
-                umma_commit(dkv_full);
+        } else {
+            // ---- accumulating MMAs: dV(t) as soon as P~(t) is in shared memory, dK / dQ(t) as soon as dS(t) is.  kv_empty / dkv_full are
+            // committed here: dS of the tile's last pair exists only after every S / dP MMA of the tile has been consumed, so when the
+            // last dK / dQ retire nothing of either issuer still reads K_j / V_j.
+            for (int j = 0; j < nk; ++j) {
+                if (j == 1) nk = tiles_to_do();
+                if (j >= nk) break;
+                wait(kv_full, j); TR(10, j);
+                if (j >= 1) { wait(dkv_read, j - 1); TR(11, j); }
+                for (int i = 0; i < n; ++i) {
+                    const int t = j * n + i;
+                    if (j == 0) wait(&q_full[i], 0);
+                    wait(p_full, t); TR(19, t);
+                    issue_dv(i); TR(20, t);
+                    wait(ds_full, t); TR(23, t);
+                    issue_dkdq(i, j); TR(24, t);
+                }
+                if (elect_one()) {
+                    umma_commit(kv_empty);
+                    umma_commit(dkv_full);
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
+        TR_END();
     } else {
         // ===================== compute warps =====================
         const int q4 = warp & 3;                                // TMEM lane quarter (hardware rule: warp id % 4)
@@ -619,6 +666,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         }
         named_bar_sync(1, BWD_COMPUTE_WARPS * 32);
         const int nk = tiles_to_do();
+        TR(30, 0);
         const long long bh = (long long)b * p.A + h;
         const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS);
         const unsigned long long seed = effective_seed(p.seed, p.seed_dev);
@@ -639,13 +687,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
                 uint32_t km[16];                 // keep-masks of my 32 columns (bf16x2 AND-masks)
                 uint32_t v[32];
                 // ---- P = exp2(S * scale + mask - lse)
+                TR(31, t);
                 mbar_wait(&s_full[g], ph);
+                TR(32, t);
                 tc_fence_after();
                 tmem_ld32(tmem_S + lane_addr + c * 32, v);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s_free[g]);         // the S columns may be overwritten (other half / next pair)
+                TR(33, t);
                 {
                     float e[32];
                     if (masked) {
@@ -670,7 +721,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
                     for (int k = 0; k < 16; ++k) pk[k] = pack_bf16(e[2 * k], e[2 * k + 1]);
                 }
                 if (p.drop_on != 0u) attn_dropout_masks16(seed, p.drop_stream, drop_row >> 5, p.drop_k2, km);
+                TR(34, t);
                 if (t >= 1) { mbar_wait(dv_done, ph ^ 1u); tc_fence_after(); }          // dV(t-1) retired: sP may be overwritten
+                TR(35, t);
                 // P~ = keep-mask AND P: the 1/(1-p) factor is folded into the dV drain and into the dS constants below
                 if (p.drop_on != 0u) {
 #pragma unroll
@@ -685,14 +738,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(p_full);
+                TR(36, t);
                 // ---- dS = [ (mask & P) * dP / (1-p) - P * delta ] * scale
                 mbar_wait(&dp_full[g], ph);
+                TR(37, t);
                 tc_fence_after();
                 tmem_ld32(tmem_dP + lane_addr + c * 32, v);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&dp_free[g]);
+                TR(38, t);
                 uint32_t ds[16];
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
@@ -703,16 +759,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
                     ffma2(d0, d1, t0, t1, c1, c1, u0, u1);
                     ds[k] = pack_bf16(d0, d1);
                 }
+                TR(39, t);
                 if (t >= 1) { mbar_wait(pair_done, ph ^ 1u); tc_fence_after(); }        // dK / dQ(t-1) retired: sdS may be overwritten
+                TR(40, t);
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                     st_shared_v4(adS + pt_offset(r, kc + q * 8), ds[q * 4], ds[q * 4 + 1], ds[q * 4 + 2], ds[q * 4 + 3]);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(ds_full);
+                TR(41, t);
             }
             // ---- dV_j, dK_j complete: group 0 drains dK, group 1 drains dV (32 columns per warp)
             mbar_wait(dkv_full, j & 1);
+            TR(42, j);
             tc_fence_after();
             {
                 const long long tok = (long long)b * p.tok_stride_b + (long long)(j * TQ + r) * p.tok_stride_s;
@@ -739,6 +799,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(dkv_read);
+            TR(43, j);
         }
         // ---- skipped (fully masked) kv tiles: zero dK / dV rows
         for (int j = nk; j < n; ++j) {
@@ -767,10 +828,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
                 atomicAdd(p.dbias + h * HD + hf * 32 + lane, cs);
             }
         }
+        TR(44, 0);
+        TR_END();
     }
     tc_fence_before();
     __syncthreads();
     if (warp == BWD_WARP_TMA) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+#ifdef DLE_ATTN_TRACE
+    if (threadIdx.x == 0 && cta_lin < TRACE_MAX_CTAS) g_attn_cta[cta_lin][2] = global_timer_ns();
+#endif
 }
 
 }  // namespace dle
@@ -869,3 +935,14 @@ extern "C" int dle_attn_bwd(const void* qkv, const float* mask, const void* ctx,
     DLE_LAUNCH_CHECK();
     return DLE_OK;
 }
+
+#ifdef DLE_ATTN_TRACE
+// measurement-only (trace variant): copies the device trace buffers to host memory
+extern "C" int dle_debug_attn_trace(unsigned long long* events /*[4][4096]*/, int* counts /*[4]*/, unsigned long long* ctas /*[8192][3]*/) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return DLE_ERR_CUDA;
+    if (cudaMemcpyFromSymbol(events, dle::g_attn_trace, sizeof(unsigned long long) * 4 * dle::TRACE_CAP) != cudaSuccess) return DLE_ERR_CUDA;
+    if (cudaMemcpyFromSymbol(counts, dle::g_attn_trace_n, sizeof(int) * 4) != cudaSuccess) return DLE_ERR_CUDA;
+    if (cudaMemcpyFromSymbol(ctas, dle::g_attn_cta, sizeof(unsigned long long) * 3 * dle::TRACE_MAX_CTAS) != cudaSuccess) return DLE_ERR_CUDA;
+    return DLE_OK;
+}
+#endif

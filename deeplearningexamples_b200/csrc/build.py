@@ -80,3 +80,5 @@ if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose=True)
     if "--variant-hint" in sys.argv:
         print("built", build_variant("hint", ["-DDLE_MBAR_HINT_NS=0x989680"]))
+    if "--variant-trace" in sys.argv:      # attention-backward hand-off timeline (tools/attn_trace.py)
+        print("built", build_variant("trace", ["-DDLE_ATTN_TRACE"]))

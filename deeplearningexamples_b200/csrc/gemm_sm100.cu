@@ -21,20 +21,28 @@ namespace dle {
 constexpr int BM = 128;
 constexpr int BK = 64;        // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 384;      // warps 0..7 epilogue, 8 TMA, 9 MMA, 10 TMEM alloc, 11 spare.  The single-issuer warps carry the HIGHEST
-                                       // warp ids: the SM sub-partition arbiter favours higher warp ids, and a starved MMA issuer idles the tensor pipe
-constexpr int WARP_TMA = 8, WARP_MMA = 9, WARP_ALLOC = 10;
-constexpr int GEMM_EPI_THREADS = 256;
-
-template <int BN> struct GemmCfg {
+// Epilogue warps (template parameter EW): 8 (two per TMEM lane quarter, each draining half the columns) or 16 (four per quarter, a
+// quarter of the columns each, 3 pipeline stages instead of 4 to pay for their staging tiles, <= 104 registers per thread).
+// Measured at T = 65536 (profiles/r02_gemm_microbench_run7_*.log): 16 warps lift the gelu'(u)-times-dgrad epilogue (817 instructions per
+// 32x32 chunk, the accumulator waiting on the epilogue) from 950 to 1055 TFLOP/s, and cost every other shape 3-15 % -- the third stage
+// alone costs the K = 4096 shapes 8 % -- so only DLE_EPI_DGELU launches take the 16-warp instance.
+// Warp roles: epilogue warps 0..EW-1, then TMA, MMA, TMEM alloc (+ a spare with 8).  The single-issuer warps carry the HIGHEST
+// warp ids: the SM sub-partition arbiter favours higher warp ids, and a starved MMA issuer idles the tensor pipe.
+template <int BN, int EW> struct GemmCfg {
+    static_assert(EW == 8 || EW == 16, "epilogue warps: 8 or 16");
+    static constexpr int EPI_WARPS = EW;
+    static constexpr int EPI_PARTS = EW / 4;                        // column parts per tile (one per warp of a quarter)
+    static constexpr int THREADS = (EW == 8) ? 384 : 608;
+    static constexpr int WARP_TMA = EW, WARP_MMA = EW + 1, WARP_ALLOC = EW + 2;
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int STAGES = (BN == 256) ? (EW == 8 ? 4 : 3) : (EW == 8 ? 6 : 4);
     static constexpr int TMEM_COLS = 2 * BN;            // double-buffered accumulator
     // epilogue: per warp a 2 KB output staging tile + a 2 KB cp.async landing tile for the residual / pre-activation operand,
     // plus 3 x 2 x 256 B of bias staging (triple-buffered per tile, one slice per column half)
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 8 * 2048 + 8 * 2048 + 1536 + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * 2048 + EPI_WARPS * 2048 + 1536 + 1024 /*align slack*/ + 256 /*barriers*/;
+    static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
 struct GemmKernelParams {
@@ -69,7 +77,7 @@ struct GemmKernelParams {
 // chunk (8.5 % of the bias+GELU epilogue's samples).  fp32 outputs (split-K atomics, logits) keep the direct path.
 // ----------------------------------------------------------------------------------------------
 constexpr int EPI_TILE_BYTES = 32 * 64;                 // per epilogue warp, out and aux each
-constexpr int EPI_BIAS_BYTES = 3 * 2 * 256;             // [tile % 3][column half][<=128 bf16]
+constexpr int EPI_BIAS_BYTES = 3 * 512;                 // [tile % 3][column part][BN / EPI_PARTS bf16], BN <= 256
 
 __device__ __forceinline__ uint32_t epi_off(int row, int unit) { return (uint32_t)(row * 64 + ((unit ^ ((row >> 1) & 3)) << 4)); }
 
@@ -85,6 +93,19 @@ __device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// EPL (1, 2 or 4) consecutive bias values of one lane: global -> registers -> the staged slice
+template <int EPL> __device__ __forceinline__ uint2 bias_load(const bf16* src) {
+    uint2 r = make_uint2(0u, 0u);
+    if constexpr (EPL == 4) r = *reinterpret_cast<const uint2*>(src);
+    else if constexpr (EPL == 2) r.x = *reinterpret_cast<const uint32_t*>(src);
+    else r.x = *reinterpret_cast<const unsigned short*>(src);
+    return r;
+}
+template <int EPL> __device__ __forceinline__ void bias_stage(uint32_t slice, int lane, uint2 b) {
+    if constexpr (EPL == 4) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(slice + lane * 8), "r"(b.x), "r"(b.y) : "memory");
+    else if constexpr (EPL == 2) asm volatile("st.shared.b32 [%0], %1;" ::"r"(slice + lane * 4), "r"(b.x) : "memory");
+    else asm volatile("st.shared.u16 [%0], %1;" ::"r"(slice + lane * 2), "h"((unsigned short)b.x) : "memory");
+}
 
 // start the copy of rows [row_base, +32) x cols [col0, +32) of the bf16 aux matrix into this warp's aux tile
 __device__ __forceinline__ void aux_prefetch(const GemmKernelParams& p, long long row_base, int col0, uint32_t aux_tile, int lane) {
@@ -236,15 +257,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
 // ----------------------------------------------------------------------------------------------
 // kernel
 // ----------------------------------------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, bool A_MN, bool B_MN, int EW>
+__global__ void __launch_bounds__((GemmCfg<BN, EW>::THREADS), 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmKernelParams p) {
-    using Cfg = GemmCfg<BN>;
+    using Cfg = GemmCfg<BN, EW>;
+    constexpr int EPI_WARPS = Cfg::EPI_WARPS, EPI_PARTS = Cfg::EPI_PARTS;
+    constexpr int WARP_TMA = Cfg::WARP_TMA, WARP_MMA = Cfg::WARP_MMA, WARP_ALLOC = Cfg::WARP_ALLOC;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* epi_stage = smem + Cfg::STAGES * Cfg::STAGE_BYTES;                 // 8 warps x (out tile, aux tile), then the bias slices
-    uint8_t* epi_bias = epi_stage + 16 * EPI_TILE_BYTES;
+    uint8_t* epi_bias = epi_stage + 2 * EPI_WARPS * EPI_TILE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(epi_bias + EPI_BIAS_BYTES);
     uint64_t* full_bar = bars;                         // [STAGES]  TMA -> MMA
     uint64_t* empty_bar = bars + Cfg::STAGES;          // [STAGES]  MMA -> TMA
@@ -259,7 +282,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], GEMM_EPI_THREADS / 32); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == WARP_ALLOC) { tmem_alloc(tmem_ptr, Cfg::TMEM_COLS); tmem_relinquish(); }
@@ -347,11 +370,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 __syncwarp();
             }
         }
-    } else if (warp < 8) {
+    } else if (warp < EPI_WARPS) {
         // ===================== epilogue warps (TMEM -> registers -> global) =====================
         const int q = warp & 3;                          // TMEM lane quarter this warp may access (hardware rule: warp id % 4)
-        const int half = warp >> 2;                      // two warps share a quarter: each drains half the columns
-        constexpr int CH = BN / 64;                      // chunks per warp per tile
+        const int half = warp >> 2;                      // column part: the EPI_PARTS warps of a quarter each drain BN / EPI_PARTS columns
+        constexpr int PART_COLS = BN / EPI_PARTS;        // columns per warp per tile
+        constexpr int CH = PART_COLS / 32;               // 32-column chunks per warp per tile
+        constexpr int EPL = PART_COLS / 32;              // bias elements staged per lane (1, 2 or 4)
+        constexpr int SLICE = PART_COLS * 2;             // bytes of one staged bias slice
         const uint32_t out_tile = smem_u32(epi_stage) + warp * 2 * EPI_TILE_BYTES;
         const uint32_t aux_tile = out_tile + EPI_TILE_BYTES;
         const unsigned long long seed = (p.drop_thresh != 0u) ? effective_seed(p.seed, p.seed_dev) : 0ull;
@@ -360,7 +386,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (use_aux && (int)blockIdx.x < total_units) {  // operand of the very first chunk
             const int tile = blockIdx.x / p.splits;
             const int m_blk = tile / p.n_tiles, n_blk = tile - m_blk * p.n_tiles;
-            aux_prefetch(p, (long long)m_blk * BM + q * 32, n_blk * BN + half * (BN / 2), aux_tile, lane);
+            aux_prefetch(p, (long long)m_blk * BM + q * 32, n_blk * BN + half * PART_COLS, aux_tile, lane);
         }
         int it = 0;
         for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++it) {
@@ -371,24 +397,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             // and stored after its last chunk, so the global latency never sits in front of the accumulator (in the epilogue-bound
             // regime the accumulator is already waiting).  The four warps of a half write the same values into the same slice; slices
             // rotate over three tiles because a warp can run at most one tile ahead of a sibling (tmem_empty needs all eight arrivals).
-            const uint32_t bias_s = smem_u32(epi_bias) + ((it % 3) * 2 + half) * 256;
-            const uint32_t bias_next = smem_u32(epi_bias) + (((it + 1) % 3) * 2 + half) * 256;
+            const uint32_t bias_s = smem_u32(epi_bias) + ((it % 3) * EPI_PARTS + half) * SLICE;
+            const uint32_t bias_next = smem_u32(epi_bias) + (((it + 1) % 3) * EPI_PARTS + half) * SLICE;
             uint2 bnext = make_uint2(0u, 0u);
             const bool has_next = p.bias != nullptr && unit + (int)gridDim.x < total_units;
             if (p.bias != nullptr) {
                 if (it == 0) {
                     uint2 b0 = make_uint2(0u, 0u);
-                    const int col = n_blk * BN + half * (BN / 2) + lane * (BN / 64);
-                    if (col < p.N) { if constexpr (BN == 256) b0 = *reinterpret_cast<const uint2*>(p.bias + col); else b0.x = *reinterpret_cast<const uint32_t*>(p.bias + col); }
-                    if constexpr (BN == 256) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(bias_s + lane * 8), "r"(b0.x), "r"(b0.y) : "memory");
-                    else asm volatile("st.shared.b32 [%0], %1;" ::"r"(bias_s + lane * 4), "r"(b0.x) : "memory");
+                    const int col = n_blk * BN + half * PART_COLS + lane * EPL;
+                    if (col < p.N) b0 = bias_load<EPL>(p.bias + col);
+                    bias_stage<EPL>(bias_s, lane, b0);
                     __syncwarp();
                 }
                 if (has_next) {
                     const int tile2 = (unit + (int)gridDim.x) / p.splits;
                     const int n2 = tile2 - (tile2 / p.n_tiles) * p.n_tiles;
-                    const int col = n2 * BN + half * (BN / 2) + lane * (BN / 64);
-                    if (col < p.N) { if constexpr (BN == 256) bnext = *reinterpret_cast<const uint2*>(p.bias + col); else bnext.x = *reinterpret_cast<const uint32_t*>(p.bias + col); }
+                    const int col = n2 * BN + half * PART_COLS + lane * EPL;
+                    if (col < p.N) bnext = bias_load<EPL>(p.bias + col);
                 }
             }
             mbar_wait(&tmem_full[acc], acc_phase);
@@ -408,7 +433,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                     } else if (unit + (int)gridDim.x < total_units) {
                         const int tile2 = (unit + (int)gridDim.x) / p.splits;
                         const int m2 = tile2 / p.n_tiles, n2 = tile2 - m2 * p.n_tiles;
-                        aux_prefetch(p, (long long)m2 * BM + q * 32, n2 * BN + half * (BN / 2), aux_tile, lane);
+                        aux_prefetch(p, (long long)m2 * BM + q * 32, n2 * BN + half * PART_COLS, aux_tile, lane);
                     }
                 } else {
 #pragma unroll
@@ -421,8 +446,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);    // one arrival per epilogue warp
             if (has_next) {
-                if constexpr (BN == 256) asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(bias_next + lane * 8), "r"(bnext.x), "r"(bnext.y) : "memory");
-                else asm volatile("st.shared.b32 [%0], %1;" ::"r"(bias_next + lane * 4), "r"(bnext.x) : "memory");
+                bias_stage<EPL>(bias_next, lane, bnext);
                 __syncwarp();
             }
         }
@@ -477,9 +501,9 @@ static int num_sms() {
     return sms[dev];
 }
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm(const dle_gemm_args* a, cudaStream_t stream) {
-    using Cfg = GemmCfg<BN>;
+template <int BN, bool A_MN, bool B_MN, int EW>
+static int launch_gemm_ew(const dle_gemm_args* a, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN, EW>;
     CUtensorMap ta, tb;
     int rc;
     // K-major operand: matrix [rows, K] -> box {64 (k), rows_per_tile}; MN-major: matrix [K, rows] -> box {64 (m/n), 64 (k)}
@@ -513,7 +537,7 @@ static int launch_gemm(const dle_gemm_args* a, cudaStream_t stream) {
     p.alpha = a->alpha;
     p.colsum_out = reinterpret_cast<float*>(a->colsum_out);
 
-    auto kern = gemm_bf16_tcgen05_kernel<BN, A_MN, B_MN>;
+    auto kern = gemm_bf16_tcgen05_kernel<BN, A_MN, B_MN, EW>;
     static bool attr_set[64] = {};                      // the attribute is per device (and per template instance)
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return DLE_ERR_CUDA;
@@ -524,9 +548,16 @@ static int launch_gemm(const dle_gemm_args* a, cudaStream_t stream) {
     }
     const int units = p.m_tiles * p.n_tiles * p.splits;
     const int grid = units < num_sms() ? units : num_sms();
-    kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
     DLE_LAUNCH_CHECK();
     return DLE_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const dle_gemm_args* a, cudaStream_t stream) {
+    // 16 epilogue warps only where they pay (see GemmCfg): the gelu'(u) epilogue on the 256-wide tile
+    if (BN == 256 && a->epilogue == DLE_EPI_DGELU) return launch_gemm_ew<BN, A_MN, B_MN, (BN == 256 ? 16 : 8)>(a, stream);
+    return launch_gemm_ew<BN, A_MN, B_MN, 8>(a, stream);
 }
 
 }  // namespace dle

@@ -13,7 +13,6 @@ from . import _lib as L
 from . import kernels as K
 
 bf16 = torch.bfloat16
-_FFN1_BIAS_GRAD_SEPARATE = __import__("os").environ.get("DLE_FFN1_BIAS_GRAD", "") == "separate"
 
 # -------------------------------------------------------------------------------------------------
 # RNG bookkeeping for dropout: one 64-bit seed per forward call site, drawn from a host counter.
@@ -308,11 +307,7 @@ class BertLayerFn(torch.autograd.Function):
         # ---- BertOutput
         dz2, dh2, dg2, dbe2, db2 = K.add_ln_bwd(dy2.contiguous(), z2, mean2, rstd2, w16(g2), dropout_p=p_hid, seed=seed_2,
                                                 dropout_stream=sid_h2, out_dtype=g2.dtype, seed_dev=sdev)
-        if _FFN1_BIAS_GRAD_SEPARATE:      # A/B switch (DLE_FFN1_BIAS_GRAD=separate): column sums of du by their own HBM-bound pass
-            du = K.gemm(dh2, w16(w2), b_layout=L.LAYOUT_MN, epilogue=L.EPI_DGELU, aux=u)
-            db1_acc.copy_(K.colsum(du))
-        else:
-            du = K.gemm(dh2, w16(w2), b_layout=L.LAYOUT_MN, epilogue=L.EPI_DGELU, aux=u, colsum_out=db1_acc)   # dgrad * gelu'(u)
+        du = K.gemm(dh2, w16(w2), b_layout=L.LAYOUT_MN, epilogue=L.EPI_DGELU, aux=u, colsum_out=db1_acc)   # dgrad * gelu'(u)
         dw2 = wgrad(dh2, g, w2.dtype)
         # ---- BertIntermediate (+ residual branch of BertOutput folded into the epilogue)
         dy1 = K.gemm(du, w16(w1), b_layout=L.LAYOUT_MN, epilogue=L.EPI_ADD, aux=dz2)
