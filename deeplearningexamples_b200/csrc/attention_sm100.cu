@@ -79,6 +79,10 @@ struct AttnFwdParams {
 // S is produced in two 64-key halves (one N = 64 MMA group per softmax half) and each half's TMEM columns are handed back as soon as the
 // owning warps hold them in registers for the exponentials (s_free): S_{j+1} is then computed by the tensor core WHILE chunk j's
 // exponentials run, instead of after them (v3a: 20 % of all stall samples were the softmax warps waiting for S).
+// staging tile of a drain: 128 rows x 128 B, 16-byte units XOR-swizzled by the row so that both the row-per-lane writes and the
+// 8-lanes-per-row reads are conflict-free
+__device__ __forceinline__ uint32_t drain_off(int row, int unit) { return (uint32_t)(row * 128 + ((unit ^ (row & 7)) << 4)); }
+
 __global__ void __launch_bounds__(FWD_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -348,18 +352,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdParam
         named_bar_sync(1 + q4, 64);
         const float l_tot = l0 + xl[(hf ^ 1) * TQ + r];
         const float inv_l = p.drop_scale / l_tot;
-        const long long tok = (long long)b * p.tok_stride_b + (long long)(qt * TQ + r) * p.tok_stride_s;
-        bf16* o = p.ctx + tok * p.H + h * HD + hf * 32;
         {
+            // O rows go through the (idle) P~ buffer so that every global store instruction covers 4 rows x 128 contiguous bytes instead of
+            // 32 lines 2 KB apart (see the backward drains): the stores of one CTA no longer hold the SM's LSU while the other CTA runs
+            const uint32_t stage = smem_u32(sP) + 2048;                // past the 1 KB row-sum exchange above
             uint32_t v[32];
             tmem_ld32(tO, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; i += 8)
-                st_global_v4(o + i, pack_bf16(__uint_as_float(v[i]) * inv_l, __uint_as_float(v[i + 1]) * inv_l),
-                             pack_bf16(__uint_as_float(v[i + 2]) * inv_l, __uint_as_float(v[i + 3]) * inv_l),
-                             pack_bf16(__uint_as_float(v[i + 4]) * inv_l, __uint_as_float(v[i + 5]) * inv_l),
-                             pack_bf16(__uint_as_float(v[i + 6]) * inv_l, __uint_as_float(v[i + 7]) * inv_l));
+            for (int k = 0; k < 4; ++k)
+                st_shared_v4(stage + drain_off(r, 4 * hf + k), pack_bf16(__uint_as_float(v[8 * k]) * inv_l, __uint_as_float(v[8 * k + 1]) * inv_l),
+                             pack_bf16(__uint_as_float(v[8 * k + 2]) * inv_l, __uint_as_float(v[8 * k + 3]) * inv_l),
+                             pack_bf16(__uint_as_float(v[8 * k + 4]) * inv_l, __uint_as_float(v[8 * k + 5]) * inv_l),
+                             pack_bf16(__uint_as_float(v[8 * k + 6]) * inv_l, __uint_as_float(v[8 * k + 7]) * inv_l));
+            named_bar_sync(5, FWD_SOFTMAX_WARPS * 32);
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int row = warp * 16 + it * 4 + (lane >> 3), ch = lane & 7;
+                const uint4 w = lds_u4(stage + drain_off(row, ch));
+                const long long tok = (long long)b * p.tok_stride_b + (long long)(qt * TQ + row) * p.tok_stride_s;
+                st_global_v4(p.ctx + tok * p.H + h * HD + ch * 8, w.x, w.y, w.z, w.w);
+            }
         }
         if (hf == 0) p.lse[((long long)b * p.A + h) * S + qt * TQ + r] = (m_run + log2f(l_tot)) * LN2;
     }
@@ -404,31 +417,35 @@ struct AttnBwdParams {
 
 __host__ __device__ inline int bwd_smem_bytes(int S) {
     const int n = S / TQ;
-    return 2 * TILE_BYTES /*K,V*/ + 2 * n * TILE_BYTES /*Q,dO of every query tile*/ + 2 * PT_BYTES /*P,dS*/ + S * 4 + 256;
+    return 4 * TILE_BYTES /*K,V x 2 slots*/ + n * TILE_BYTES /*Q of every query tile*/ + 2 * TILE_BYTES /*dO ring*/ + 2 * PT_BYTES /*P,dS*/ + S * 4 + 256;
 }
 
-// delta[b,h,s] = sum_d dO[t, h*64+d] * O[t, h*64+d]
+// delta[b,h,s] = sum_d dO[t, h*64+d] * O[t, h*64+d].  Eight lanes share one (token, head) row: consecutive lanes read consecutive 16-byte
+// units, so a warp instruction covers 4 whole 128-byte lines (one thread per row touched 32 lines per instruction and ran at 3.7 TB/s).
 __global__ void attn_delta_kernel(const bf16* __restrict__ dctx, const bf16* __restrict__ ctx, float* __restrict__ delta,
                                   int B, int S, int A, int seq_first) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // token * A + h
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long idx = gid >> 3;                                            // token * A + h
+    const int unit = (int)(gid & 7);
     const long long total = (long long)B * S * A;
-    if (idx >= total) return;
-    const long long tok = idx / A; const int h = (int)(idx - tok * A);
-    const bf16* a = dctx + tok * (long long)(A * HD) + h * HD;
-    const bf16* c = ctx + tok * (long long)(A * HD) + h * HD;
     float acc = 0.f;
-#pragma unroll
-    for (int i = 0; i < HD; i += 8) {
-        uint4 ua = ld_global_nc_v4(a + i), uc = ld_global_nc_v4(c + i);
+    if (idx < total) {
+        const uint4 ua = ld_global_nc_v4(dctx + idx * HD + unit * 8), uc = ld_global_nc_v4(ctx + idx * HD + unit * 8);
         float2 x, y;
         x = unpack_bf16(ua.x); y = unpack_bf16(uc.x); acc += x.x * y.x + x.y * y.y;
         x = unpack_bf16(ua.y); y = unpack_bf16(uc.y); acc += x.x * y.x + x.y * y.y;
         x = unpack_bf16(ua.z); y = unpack_bf16(uc.z); acc += x.x * y.x + x.y * y.y;
         x = unpack_bf16(ua.w); y = unpack_bf16(uc.w); acc += x.x * y.x + x.y * y.y;
     }
-    const int b = seq_first ? (int)(tok % B) : (int)(tok / S);
-    const int s = seq_first ? (int)(tok / B) : (int)(tok - (long long)b * S);
-    delta[((long long)b * A + h) * S + s] = acc;
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (idx < total && unit == 0) {
+        const long long tok = idx / A; const int h = (int)(idx - tok * A);
+        const int b = seq_first ? (int)(tok % B) : (int)(tok / S);
+        const int s_ = seq_first ? (int)(tok / B) : (int)(tok - (long long)b * S);
+        delta[((long long)b * A + h) * S + s_] = acc;
+    }
 }
 
 // Measurement-only build switch (-DDLE_ATTN_TRACE, csrc/build.py --variant-trace): lane 0 of the MMA warp and of one compute warp per group
@@ -450,30 +467,33 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do, const AttnBwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int S = p.S, n = S / TQ;
-    uint8_t* sK = smem;
-    uint8_t* sV = sK + TILE_BYTES;
-    uint8_t* sQ = sV + TILE_BYTES;               // [n]
-    uint8_t* sdO = sQ + n * TILE_BYTES;          // [n]
-    uint8_t* sP = sdO + n * TILE_BYTES;
+    uint8_t* sK = smem;                          // [2]  kv tile j lives in slot j & 1
+    uint8_t* sV = sK + 2 * TILE_BYTES;           // [2]
+    uint8_t* sQ = sV + 2 * TILE_BYTES;           // [n]  resident for the whole head
+    uint8_t* sdO = sQ + n * TILE_BYTES;          // [2]  ring: the dO tile of pair t lives in slot t & 1
+    uint8_t* sP = sdO + 2 * TILE_BYTES;
     uint8_t* sdS = sP + PT_BYTES;
     float* sMask = reinterpret_cast<float*>(sdS + PT_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sMask + S);
-    uint64_t* kv_full = bars;         // 1
-    uint64_t* kv_empty = bars + 1;    // 1
-    uint64_t* q_full = bars + 2;      // [4]  Q_i and dO_i landed (once per head)
-    uint64_t* s_full = bars + 6;      // [2]  S half g in TMEM            (per pair)
-    uint64_t* dp_full = bars + 8;     // [2]  dP half g in TMEM           (per pair)
-    uint64_t* s_free = bars + 10;     // [2]  group g has S half g in registers   (8 warp arrivals per pair)
-    uint64_t* dp_free = bars + 12;    // [2]
-    uint64_t* p_full = bars + 14;     // P~ tile complete in smem         (16 warp arrivals per pair)
-    uint64_t* ds_full = bars + 15;    // dS tile complete in smem         (16)
-    uint64_t* dv_done = bars + 16;    // dV(t) retired: sP may be rewritten
-    uint64_t* pair_done = bars + 17;  // dK(t), dQ(t) retired: sdS may be rewritten
-    uint64_t* dkv_full = bars + 18;   // kv tile finished: dK, dV (and at the end dQ) complete
-    uint64_t* dkv_read = bars + 19;   // accumulators drained (16)
-    uint64_t* nk_ready = bars + 20;   // number of kv tiles to process is known (16 compute-warp arrivals)
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 21);
-    int* s_nk = reinterpret_cast<int*>(bars + 21) + 1;      // kv tiles that hold at least one attendable key
+    uint64_t* kv_full = bars;         // [2]  K_j, V_j landed in slot j & 1   (completion j >> 1 of that slot)
+    uint64_t* kv_empty = bars + 2;    // [2]  every MMA that reads the slot has retired
+    uint64_t* q_full = bars + 4;      // [4]  Q_i landed (once per head)
+    uint64_t* s_full = bars + 8;      // [2]  S half g in TMEM            (per pair)
+    uint64_t* dp_full = bars + 10;    // [2]  dP half g in TMEM           (per pair)
+    uint64_t* s_free = bars + 12;     // [2]  group g has S half g in registers   (8 warp arrivals per pair)
+    uint64_t* dp_free = bars + 14;    // [2]
+    uint64_t* p_full = bars + 16;     // P~ tile complete in smem         (16 warp arrivals per pair)
+    uint64_t* ds_full = bars + 17;    // dS tile complete in smem         (16)
+    uint64_t* dv_done = bars + 18;    // dV(t) retired: sP may be rewritten
+    uint64_t* pair_done = bars + 19;  // dK(t), dQ(t) retired: sdS may be rewritten
+    uint64_t* dkv_full = bars + 20;   // kv tile finished: dK, dV (and at the end dQ) complete
+    uint64_t* dkv_read = bars + 21;   // accumulators drained (16)
+    uint64_t* nk_ready = bars + 22;   // number of kv tiles to process is known (16 compute-warp arrivals)
+    uint64_t* do_full = bars + 23;    // [2]  dO tile of pair t landed in slot t & 1   (completion t >> 1 of that slot)
+    uint64_t* do_empty = bars + 25;   // [2]  2 arrivals: dP(t, 1) retired (S/dP issuer) and dV(t) retired (accumulating issuer)
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 27);
+    int* s_nk = reinterpret_cast<int*>(bars + 27) + 1;      // kv tiles that hold at least one attendable key
+    volatile int* s_nk_loop = reinterpret_cast<volatile int*>(bars + 28);   // the compute warps' loop bound, re-read from here (see below)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = blockIdx.x, b = blockIdx.y;
@@ -491,7 +511,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     if (threadIdx.x == 0) {
         if ((smem_u32(smem) & 1023u) != 0) __trap();          // SWIZZLE_128B tiles need a 1024-byte aligned base
         tma_prefetch_desc(&tmap_qkv); tma_prefetch_desc(&tmap_do);
-        mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&do_full[i], 1); mbar_init(&do_empty[i], 2); }
         for (int i = 0; i < 4; ++i) mbar_init(&q_full[i], 1);
         for (int g = 0; g < 2; ++g) {
             mbar_init(&s_full[g], 1); mbar_init(&dp_full[g], 1);
@@ -523,36 +543,58 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     // Producer and MMA warps: warp-uniform loops (all lanes wait), tcgen05 / TMA instructions under elect_one() -- see gemm_sm100.cu.
     if (warp == BWD_WARP_TMA) {
         // ===================== TMA producer =====================
+        // K_j / V_j are double-buffered (tile j+1 is fetched while tile j is processed: the trace showed the single buffer costing ~6000 clk
+        // per kv tile -- drain of the last MMAs, then 32 KB of TMA, then the first S -- a quarter of the kernel), and the room comes from
+        // streaming dO through a two-slot ring instead of keeping it resident beside Q.
+        auto load_kv = [&](int j_) {
+            const int sl = j_ & 1;
+            mbar_expect_tx(&kv_full[sl], 2 * TILE_BYTES);
+            tma_load_3d(sK + sl * TILE_BYTES, &tmap_qkv, &kv_full[sl], p.H + h * HD, j_ * TQ, b);
+            tma_load_3d(sV + sl * TILE_BYTES, &tmap_qkv, &kv_full[sl], 2 * p.H + h * HD, j_ * TQ, b);
+        };
+        auto load_do = [&](int u_) {                         // dO tile of pair u_ (query tile u_ % n)
+            const int sl = u_ & 1;
+            mbar_expect_tx(&do_full[sl], TILE_BYTES);
+            tma_load_3d(sdO + sl * TILE_BYTES, &tmap_do, &do_full[sl], h * HD, (u_ % n) * TQ, b);
+        };
         if (elect_one()) {
-            mbar_expect_tx(kv_full, 2 * TILE_BYTES);
-            tma_load_3d(sK, &tmap_qkv, kv_full, p.H + h * HD, 0, b);
-            tma_load_3d(sV, &tmap_qkv, kv_full, 2 * p.H + h * HD, 0, b);
-            for (int i = 0; i < n; ++i) {
-                mbar_expect_tx(&q_full[i], 2 * TILE_BYTES);
+            load_kv(0);
+            mbar_expect_tx(&q_full[0], TILE_BYTES);
+            tma_load_3d(sQ, &tmap_qkv, &q_full[0], h * HD, 0, b);
+            load_do(0);
+            for (int i = 1; i < n; ++i) {
+                mbar_expect_tx(&q_full[i], TILE_BYTES);
                 tma_load_3d(sQ + i * TILE_BYTES, &tmap_qkv, &q_full[i], h * HD, i * TQ, b);
-                tma_load_3d(sdO + i * TILE_BYTES, &tmap_do, &q_full[i], h * HD, i * TQ, b);
             }
+            if (n >= 2) load_do(1);
         }
         __syncwarp();
         const int nk = tiles_to_do();
-        for (int j = 1; j < nk; ++j) {
-            mbar_wait(kv_empty, (j - 1) & 1);                // every MMA that reads K_{j-1} / V_{j-1} has retired
-            if (elect_one()) {
-                mbar_expect_tx(kv_full, 2 * TILE_BYTES);
-                tma_load_3d(sK, &tmap_qkv, kv_full, p.H + h * HD, j * TQ, b);
-                tma_load_3d(sV, &tmap_qkv, kv_full, 2 * p.H + h * HD, j * TQ, b);
-            }
+        const int total = nk * n;
+        if (nk > 1) {
+            if (elect_one()) load_kv(1);
             __syncwarp();
+        }
+        for (int u = (n >= 2) ? 2 : 1; u < total; ++u) {
+            if (u >= 2) mbar_wait(&do_empty[u & 1], (uint32_t)((u >> 1) - 1) & 1u);     // pair u-2 no longer reads the slot
+            if (elect_one()) load_do(u);
+            __syncwarp();
+            const int j = u / n;
+            if (u - j * n == 0 && j >= 1 && j + 1 < nk) {    // tile j begins: tile j-1 is finishing, its slot takes tile j+1
+                mbar_wait(&kv_empty[(j + 1) & 1], (uint32_t)((j - 1) >> 1) & 1u);
+                if (elect_one()) load_kv(j + 1);
+                __syncwarp();
+            }
         }
     } else if (warp == BWD_WARP_MMA || warp == BWD_WARP_MMA2) {
         // ===================== MMA issuer(s) =====================
         constexpr uint32_t id_h = make_idesc_bf16(TQ, 64, false, false);      // S half, dP half: [128 q] x [64 keys], K = d
         constexpr uint32_t id_mm = make_idesc_bf16(TQ, HD, true, true);       // dV, dK
         constexpr uint32_t id_km = make_idesc_bf16(TQ, HD, false, true);      // dQ
-        const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ0 = smem_u32(sQ), adO0 = smem_u32(sdO), aP = smem_u32(sP), adS = smem_u32(sdS);
-        auto issue_s = [&](int i_, int g_) {                // S(t, g) = Q_i K_{j, half g}^T
+        const uint32_t aK0 = smem_u32(sK), aV0 = smem_u32(sV), aQ0 = smem_u32(sQ), adO0 = smem_u32(sdO), aP = smem_u32(sP), adS = smem_u32(sdS);
+        auto issue_s = [&](int i_, int j_, int g_) {        // S(t, g) = Q_i K_{j, half g}^T
             if (elect_one()) {
-                const uint32_t aQ = aQ0 + i_ * TILE_BYTES, aKh = aK + g_ * HALF_BYTES;
+                const uint32_t aQ = aQ0 + i_ * TILE_BYTES, aKh = aK0 + (j_ & 1) * TILE_BYTES + g_ * HALF_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
                     umma_bf16_ss(tmem_S, make_smem_desc_sw128(aQ + kk * 32, 0, 1024), make_smem_desc_sw128(aKh + kk * 32, 0, 1024), id_h, kk > 0 ? 1u : 0u);
@@ -560,30 +602,32 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             }
             __syncwarp();
         };
-        auto issue_dp = [&](int i_, int g_) {               // dP(t, g) = dO_i V_{j, half g}^T
+        auto issue_dp = [&](int t_, int j_, int g_) {       // dP(t, g) = dO_i V_{j, half g}^T
             if (elect_one()) {
-                const uint32_t adO = adO0 + i_ * TILE_BYTES, aVh = aV + g_ * HALF_BYTES;
+                const uint32_t adO = adO0 + (t_ & 1) * TILE_BYTES, aVh = aV0 + (j_ & 1) * TILE_BYTES + g_ * HALF_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
                     umma_bf16_ss(tmem_dP, make_smem_desc_sw128(adO + kk * 32, 0, 1024), make_smem_desc_sw128(aVh + kk * 32, 0, 1024), id_h, kk > 0 ? 1u : 0u);
                 umma_commit(&dp_full[g_]);
+                if (g_ == 1) umma_commit(&do_empty[t_ & 1]);          // this issuer's last read of the dO slot
             }
             __syncwarp();
         };
-        auto issue_dv = [&](int i_) {                       // dV_j += P~^T dO_i
+        auto issue_dv = [&](int i_, int t_) {               // dV_j += P~^T dO_i
             if (elect_one()) {
-                const uint32_t adO = adO0 + i_ * TILE_BYTES;
+                const uint32_t adO = adO0 + (t_ & 1) * TILE_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk)
                     umma_bf16_ss(tmem_dV, make_smem_desc_sw128(aP + kk * 2048, TILE_BYTES, 1024),
                                  make_smem_desc_sw128(adO + kk * 2048, TILE_BYTES, 1024), id_mm, (i_ > 0 || kk > 0) ? 1u : 0u);
                 umma_commit(dv_done);
+                umma_commit(&do_empty[t_ & 1]);
             }
             __syncwarp();
         };
         auto issue_dkdq = [&](int i_, int j_) {             // dK_j += dS^T Q_i ; dQ_i += dS K_j
             if (elect_one()) {
-                const uint32_t aQ = aQ0 + i_ * TILE_BYTES;
+                const uint32_t aQ = aQ0 + i_ * TILE_BYTES, aK = aK0 + (j_ & 1) * TILE_BYTES;
 #pragma unroll
                 for (int kk = 0; kk < 8; ++kk)
                     umma_bf16_ss(tmem_dK, make_smem_desc_sw128(adS + kk * 2048, TILE_BYTES, 1024),
@@ -603,20 +647,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             for (int j = 0; j < nk; ++j) {
                 if (j == 1) nk = tiles_to_do();
                 if (j >= nk) break;
-                wait(kv_full, j); TR(10, j);
+                wait(&kv_full[j & 1], j >> 1); TR(10, j);
                 for (int i = 0; i < n; ++i) {
                     const int t = j * n + i;
                     if (j == 0) { wait(&q_full[i], 0); TR(12, t); }
                     if (t >= 1) wait(&s_free[1], t - 1);
                     TR(13, t);
-                    issue_s(i, 0); TR(14, t);
+                    issue_s(i, j, 0); TR(14, t);
                     if (t >= 1) wait(&dp_free[1], t - 1);
+                    wait(&do_full[t & 1], t >> 1);
                     TR(15, t);
-                    issue_dp(i, 0); TR(16, t);
+                    issue_dp(t, j, 0); TR(16, t);
                     wait(&s_free[0], t); TR(17, t);
-                    issue_s(i, 1); TR(18, t);
+                    issue_s(i, j, 1); TR(18, t);
                     wait(&dp_free[0], t); TR(21, t);
-                    issue_dp(i, 1); TR(22, t);
+                    issue_dp(t, j, 1); TR(22, t);
                 }
             }
         } else {
@@ -626,18 +671,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             for (int j = 0; j < nk; ++j) {
                 if (j == 1) nk = tiles_to_do();
                 if (j >= nk) break;
-                wait(kv_full, j); TR(10, j);
+                wait(&kv_full[j & 1], j >> 1); TR(10, j);
                 if (j >= 1) { wait(dkv_read, j - 1); TR(11, j); }
                 for (int i = 0; i < n; ++i) {
                     const int t = j * n + i;
                     if (j == 0) wait(&q_full[i], 0);
-                    wait(p_full, t); TR(19, t);
-                    issue_dv(i); TR(20, t);
+                    wait(p_full, t);
+                    wait(&do_full[t & 1], t >> 1); TR(19, t);
+                    issue_dv(i, t); TR(20, t);
                     wait(ds_full, t); TR(23, t);
                     issue_dkdq(i, j); TR(24, t);
                 }
                 if (elect_one()) {
-                    umma_commit(kv_empty);
+                    umma_commit(&kv_empty[j & 1]);
                     umma_commit(dkv_full);
                 }
                 __syncwarp();
@@ -665,14 +711,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             }
         }
         named_bar_sync(1, BWD_COMPUTE_WARPS * 32);
-        const int nk = tiles_to_do();
+        // ptxas keeps this loop bound on the stack (the register budget is spent on the 32-wide row buffers), and its reload at the end of
+        // each kv tile queued behind the drain's global stores: every thread parks the value in shared memory and re-reads it from there
+        // (a thread reads back what it wrote itself, so no barrier is needed).
+        *s_nk_loop = tiles_to_do();
         TR(30, 0);
         const long long bh = (long long)b * p.A + h;
+        // per-row softmax statistics of this thread's row in every query tile, fetched once per head: the trace showed each pair opening
+        // with ~1000 clk of waiting for these two global loads (and ~4000 clk at a kv-tile boundary, behind the drain's stores / atomics)
+        float lse_r[4], dl_r[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            lse_r[i] = (i < n) ? -p.lse[bh * S + i * TQ + r] * LOG2E : 0.f;
+            dl_r[i] = (i < n) ? -p.delta[bh * S + i * TQ + r] * p.scale : 0.f;
+        }
+        float dbias_acc = 0.f;                                  // key / value bias gradient of my column, summed over the kv tiles
         const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS);
         const unsigned long long seed = effective_seed(p.seed, p.seed_dev);
         const int kc = g * 64 + c * 32;                         // first key column (within the 128-key tile) of this thread
         const float c1 = p.drop_scale * p.scale;
-        for (int j = 0; j < nk; ++j) {
+        for (int j = 0; j < *s_nk_loop; ++j) {
             // my 32 key columns of this kv tile: additive mask (already x log2e) from shared memory, skipped entirely when it is all
             // zero (warp-uniform; unpadded batches)
             const uint32_t mk_addr = smem_u32(sMask + j * TQ + kc);
@@ -680,8 +738,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             for (int i = 0; i < n; ++i) {
                 const int t = j * n + i;
                 const uint32_t ph = (uint32_t)t & 1u;
-                const float neg_lse2 = -p.lse[bh * S + i * TQ + r] * LOG2E;
-                const float nd = -p.delta[bh * S + i * TQ + r] * p.scale;
+                const float neg_lse2 = i == 0 ? lse_r[0] : i == 1 ? lse_r[1] : i == 2 ? lse_r[2] : lse_r[3];
+                const float nd = i == 0 ? dl_r[0] : i == 1 ? dl_r[1] : i == 2 ? dl_r[2] : dl_r[3];
                 const unsigned long long drop_row = (unsigned long long)(bh * S + (i * TQ + r)) * (unsigned long long)S + j * TQ + kc;
                 uint32_t pk[16];                 // undropped P, packed bf16x2 (32 values)
                 uint32_t km[16];                 // keep-masks of my 32 columns (bf16x2 AND-masks)
@@ -770,62 +828,87 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
                 if (lane == 0) mbar_arrive(ds_full);
                 TR(41, t);
             }
-            // ---- dV_j, dK_j complete: group 0 drains dK, group 1 drains dV (32 columns per warp)
+            // ---- dV_j, dK_j complete: group 0 drains dK, group 1 drains dV (32 columns per warp).  The rows go through shared memory
+            // (P~ / dS staging is idle here: every MMA of the tile has retired) so that each global store instruction covers 4 rows x 128
+            // contiguous bytes: written straight from the row-per-lane registers, every STG.128 touched 32 different lines 6 KB apart
+            // and the 2048 line writes of one drain held the LSU for ~2000 clk -- the loads that open the next pair queued behind them
+            // (trace: ~2300-4300 idle clk at every kv-tile boundary).
             mbar_wait(dkv_full, j & 1);
             TR(42, j);
             tc_fence_after();
             {
-                const long long tok = (long long)b * p.tok_stride_b + (long long)(j * TQ + r) * p.tok_stride_s;
                 uint32_t v[32];
                 tmem_ld32((g == 0 ? tmem_dK : tmem_dV) + lane_addr + c * 32, v);
                 tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(dkv_read);            // the accumulator columns are in registers: the next tile may overwrite them
                 if (g == 1 && p.drop_on != 0u) {                 // dV accumulated keep-mask AND P: apply the 1/(1-p) factor here
 #pragma unroll
                     for (int k = 0; k < 32; ++k) v[k] = __float_as_uint(__uint_as_float(v[k]) * p.drop_scale);
                 }
-                bf16* o = p.dqkv + tok * (3LL * p.H) + (g + 1) * p.H + h * HD + c * 32;
+                const uint32_t stage = (g == 0) ? adS : aP;
 #pragma unroll
-                for (int k = 0; k < 32; k += 8)
-                    st_global_v4(o + k, pack_bf16(__uint_as_float(v[k]), __uint_as_float(v[k + 1])), pack_bf16(__uint_as_float(v[k + 2]), __uint_as_float(v[k + 3])),
-                                 pack_bf16(__uint_as_float(v[k + 4]), __uint_as_float(v[k + 5])), pack_bf16(__uint_as_float(v[k + 6]), __uint_as_float(v[k + 7])));
+                for (int k = 0; k < 4; ++k)
+                    st_shared_v4(stage + drain_off(r, 4 * c + k), pack_bf16(__uint_as_float(v[8 * k]), __uint_as_float(v[8 * k + 1])),
+                                 pack_bf16(__uint_as_float(v[8 * k + 2]), __uint_as_float(v[8 * k + 3])), pack_bf16(__uint_as_float(v[8 * k + 4]), __uint_as_float(v[8 * k + 5])),
+                                 pack_bf16(__uint_as_float(v[8 * k + 6]), __uint_as_float(v[8 * k + 7])));
                 if (p.dbias != nullptr) {                        // key / value bias gradients: column sums of the stored bf16 values
                     float f[32];
 #pragma unroll
                     for (int k = 0; k < 32; ++k) f[k] = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[k])));
-                    const float cs = warp_column_sums32(f, lane);
-                    atomicAdd(p.dbias + (g + 1) * p.H + h * HD + c * 32 + lane, cs);
+                    dbias_acc += warp_column_sums32(f, lane);    // one atomic per head (below), not one per kv tile on the tile boundary
+                }
+                named_bar_sync(2 + g, BWD_GROUP_WARPS * 32);     // the group's 128 x 64 tile is staged
+                const int gw = c * 4 + q4;                       // warp index within the group: 16 rows each
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int row = gw * 16 + it * 4 + (lane >> 3), ch = lane & 7;
+                    const uint4 w = lds_u4(stage + drain_off(row, ch));
+                    const long long tok = (long long)b * p.tok_stride_b + (long long)(j * TQ + row) * p.tok_stride_s;
+                    st_global_v4(p.dqkv + tok * (3LL * p.H) + (g + 1) * p.H + h * HD + ch * 8, w.x, w.y, w.z, w.w);
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(dkv_read);
+            named_bar_sync(1, BWD_COMPUTE_WARPS * 32);           // both staging tiles are read: P~ / dS of the next pair may be written
             TR(43, j);
         }
+        if (p.dbias != nullptr) atomicAdd(p.dbias + (g + 1) * p.H + h * HD + c * 32 + lane, dbias_acc);
         // ---- skipped (fully masked) kv tiles: zero dK / dV rows
-        for (int j = nk; j < n; ++j) {
+        for (int j = *s_nk_loop; j < n; ++j) {
             const long long tok = (long long)b * p.tok_stride_b + (long long)(j * TQ + r) * p.tok_stride_s;
             bf16* o = p.dqkv + tok * (3LL * p.H) + (g + 1) * p.H + h * HD + c * 32;
 #pragma unroll
             for (int k = 0; k < 32; k += 8) st_global_v4(o + k, 0u, 0u, 0u, 0u);
         }
-        // ---- all pairs done (dkv_full of the last kv tile implies every MMA retired): drain dQ, two 32-column chunks per warp
+        // ---- all pairs done (dkv_full of the last kv tile implies every MMA retired): drain dQ, two 32-column chunks per warp, staged the
+        // same way (query tile i in the i-th 16 KB quarter of the P~ / dS staging area)
         for (int ch = wi; ch < 2 * n; ch += 4) {
             const int i = ch >> 1, hf = ch & 1;
             uint32_t v[32];
             tmem_ld32(tmem_dQ + i * HD + lane_addr + hf * 32, v);
             tmem_ld_wait();
-            const long long tok = (long long)b * p.tok_stride_b + (long long)(i * TQ + r) * p.tok_stride_s;
-            bf16* o = p.dqkv + tok * (3LL * p.H) + h * HD + hf * 32;
+            const uint32_t stage = (i < 2 ? aP : adS) + (i & 1) * (TQ * 128);
 #pragma unroll
-            for (int k = 0; k < 32; k += 8)
-                st_global_v4(o + k, pack_bf16(__uint_as_float(v[k]), __uint_as_float(v[k + 1])), pack_bf16(__uint_as_float(v[k + 2]), __uint_as_float(v[k + 3])),
-                             pack_bf16(__uint_as_float(v[k + 4]), __uint_as_float(v[k + 5])), pack_bf16(__uint_as_float(v[k + 6]), __uint_as_float(v[k + 7])));
+            for (int k = 0; k < 4; ++k)
+                st_shared_v4(stage + drain_off(r, 4 * hf + k), pack_bf16(__uint_as_float(v[8 * k]), __uint_as_float(v[8 * k + 1])),
+                             pack_bf16(__uint_as_float(v[8 * k + 2]), __uint_as_float(v[8 * k + 3])), pack_bf16(__uint_as_float(v[8 * k + 4]), __uint_as_float(v[8 * k + 5])),
+                             pack_bf16(__uint_as_float(v[8 * k + 6]), __uint_as_float(v[8 * k + 7])));
             if (p.dbias != nullptr) {                            // query bias gradient
                 float f[32];
 #pragma unroll
                 for (int k = 0; k < 32; ++k) f[k] = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[k])));
                 const float cs = warp_column_sums32(f, lane);
                 atomicAdd(p.dbias + h * HD + hf * 32 + lane, cs);
+            }
+        }
+        named_bar_sync(1, BWD_COMPUTE_WARPS * 32);
+        for (int it = 0; it < 8; ++it) {
+            const int R = warp * 32 + it * 4 + (lane >> 3), ch = lane & 7;      // row of the head's [S, 64] dQ, 16-byte unit within it
+            if (R < S) {
+                const int i = R >> 7, row = R & (TQ - 1);
+                const uint4 w = lds_u4((i < 2 ? aP : adS) + (i & 1) * (TQ * 128) + drain_off(row, ch));
+                const long long tok = (long long)b * p.tok_stride_b + (long long)R * p.tok_stride_s;
+                st_global_v4(p.dqkv + tok * (3LL * p.H) + h * HD + ch * 8, w.x, w.y, w.z, w.w);
             }
         }
         TR(44, 0);
@@ -920,7 +1003,7 @@ extern "C" int dle_attn_bwd(const void* qkv, const float* mask, const void* ctx,
     rc = make_tmap_tokens_3d(&td, dctx, B, S, H, seq_first);
     if (rc != DLE_OK) return rc;
     const long long total = (long long)B * S * A;
-    attn_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(dctx), reinterpret_cast<const bf16*>(ctx), delta_ws, B, S, A, seq_first);
+    attn_delta_kernel<<<(unsigned)((total * 8 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const bf16*>(dctx), reinterpret_cast<const bf16*>(ctx), delta_ws, B, S, A, seq_first);
     DLE_LAUNCH_CHECK();
     AttnBwdParams p;
     p.mask = mask; p.lse = lse; p.delta = delta_ws; p.dbias = dbias_qkv; p.dqkv = reinterpret_cast<bf16*>(dqkv);

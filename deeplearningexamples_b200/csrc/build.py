@@ -39,7 +39,7 @@ def _compile(src):
     return obj, False
 
 
-def build_variant(name, extra_flags):
+def build_variant(name, extra_flags, only=None):
     """A/B builds of the same ABI with different compile-time switches (e.g. -DDLE_MBAR_HINT_NS=0): deeplearningexamples_b200/libdle_b200_<name>.so,
     selected at run time with DLE_LIB_PATH (see _lib.py).  Measurement tooling only."""
     vdir = os.path.join(OBJ_DIR, "variant_" + name)
@@ -47,7 +47,8 @@ def build_variant(name, extra_flags):
     objs = []
     for src in SOURCES:
         obj = os.path.join(vdir, src.replace(".cu", ".o"))
-        r = subprocess.run([NVCC] + FLAGS + list(extra_flags) + ["-c", os.path.join(HERE, src), "-o", obj], capture_output=True, text=True)
+        fl = list(extra_flags) if (only is None or src in only) else []      # `only`: the sources the switches apply to
+        r = subprocess.run([NVCC] + FLAGS + fl + ["-c", os.path.join(HERE, src), "-o", obj], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
         objs.append(obj)
@@ -80,5 +81,7 @@ if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose=True)
     if "--variant-hint" in sys.argv:
         print("built", build_variant("hint", ["-DDLE_MBAR_HINT_NS=0x989680"]))
+    if "--variant-gemmhint" in sys.argv:   # suspend-time hint on the GEMM kernel's mbarrier waits only
+        print("built", build_variant("gemmhint", ["-DDLE_MBAR_HINT_NS=0x989680"], only=["gemm_sm100.cu"]))
     if "--variant-trace" in sys.argv:      # attention-backward hand-off timeline (tools/attn_trace.py)
         print("built", build_variant("trace", ["-DDLE_ATTN_TRACE"]))
