@@ -717,19 +717,62 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         *s_nk_loop = tiles_to_do();
         TR(30, 0);
         const long long bh = (long long)b * p.A + h;
-        // per-row softmax statistics of this thread's row in every query tile, fetched once per head: the trace showed each pair opening
-        // with ~1000 clk of waiting for these two global loads (and ~4000 clk at a kv-tile boundary, behind the drain's stores / atomics)
-        float lse_r[4], dl_r[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            lse_r[i] = (i < n) ? -p.lse[bh * S + i * TQ + r] * LOG2E : 0.f;
-            dl_r[i] = (i < n) ? -p.delta[bh * S + i * TQ + r] * p.scale : 0.f;
-        }
+        // per-row softmax statistics of this thread's row: the pair loop fetches the NEXT pair's two values while it works on the
+        // current one (the trace showed each pair opening with ~1000 clk of waiting for these loads when they were issued in place,
+        // and ~580 clk when all tiles' values were kept per thread -- they did not fit in registers and came back from local memory)
+        float lse_nxt = p.lse[bh * S + r], dl_nxt = p.delta[bh * S + r];
         float dbias_acc = 0.f;                                  // key / value bias gradient of my column, summed over the kv tiles
         const uint32_t aP = smem_u32(sP), adS = smem_u32(sdS);
         const unsigned long long seed = effective_seed(p.seed, p.seed_dev);
         const int kc = g * 64 + c * 32;                         // first key column (within the 128-key tile) of this thread
         const float c1 = p.drop_scale * p.scale;
+        // drain of a finished kv tile; called from inside the first pair of the NEXT tile (after its P is computed, before it is stored) so
+        // that the wait for the tile's last dK / dQ MMAs is covered by that pair's S -> P work, and after the loop for the last tile
+        auto drain_kv = [&](int jd) {
+            // ---- dV_j, dK_j complete: group 0 drains dK, group 1 drains dV (32 columns per warp).  The rows go through shared memory
+            // (P~ / dS staging is idle here: every MMA of the tile has retired) so that each global store instruction covers 4 rows x 128
+            // contiguous bytes: written straight from the row-per-lane registers, every STG.128 touched 32 different lines 6 KB apart
+            // and the 2048 line writes of one drain held the LSU for ~2000 clk -- the loads that open the next pair queued behind them
+            // (trace: ~2300-4300 idle clk at every kv-tile boundary).
+            mbar_wait(dkv_full, jd & 1);
+            TR(42, jd);
+            tc_fence_after();
+            {
+                uint32_t v[32];
+                tmem_ld32((g == 0 ? tmem_dK : tmem_dV) + lane_addr + c * 32, v);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(dkv_read);            // the accumulator columns are in registers: the next tile may overwrite them
+                if (g == 1 && p.drop_on != 0u) {                 // dV accumulated keep-mask AND P: apply the 1/(1-p) factor here
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) v[k] = __float_as_uint(__uint_as_float(v[k]) * p.drop_scale);
+                }
+                const uint32_t stage = (g == 0) ? adS : aP;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    st_shared_v4(stage + drain_off(r, 4 * c + k), pack_bf16(__uint_as_float(v[8 * k]), __uint_as_float(v[8 * k + 1])),
+                                 pack_bf16(__uint_as_float(v[8 * k + 2]), __uint_as_float(v[8 * k + 3])), pack_bf16(__uint_as_float(v[8 * k + 4]), __uint_as_float(v[8 * k + 5])),
+                                 pack_bf16(__uint_as_float(v[8 * k + 6]), __uint_as_float(v[8 * k + 7])));
+                if (p.dbias != nullptr) {                        // key / value bias gradients: column sums of the stored bf16 values
+                    float f[32];
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) f[k] = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[k])));
+                    dbias_acc += warp_column_sums32(f, lane);    // one atomic per head (below), not one per kv tile on the tile boundary
+                }
+                named_bar_sync(2 + g, BWD_GROUP_WARPS * 32);     // the group's 128 x 64 tile is staged
+                const int gw = c * 4 + q4;                       // warp index within the group: 16 rows each
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int row = gw * 16 + it * 4 + (lane >> 3), ch = lane & 7;
+                    const uint4 w = lds_u4(stage + drain_off(row, ch));
+                    const long long tok = (long long)b * p.tok_stride_b + (long long)(jd * TQ + row) * p.tok_stride_s;
+                    st_global_v4(p.dqkv + tok * (3LL * p.H) + (g + 1) * p.H + h * HD + ch * 8, w.x, w.y, w.z, w.w);
+                }
+            }
+            named_bar_sync(1, BWD_COMPUTE_WARPS * 32);           // both staging tiles are read: P~ / dS of the next pair may be written
+            TR(43, jd);
+        };
         for (int j = 0; j < *s_nk_loop; ++j) {
             // my 32 key columns of this kv tile: additive mask (already x log2e) from shared memory, skipped entirely when it is all
             // zero (warp-uniform; unpadded batches)
@@ -738,8 +781,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             for (int i = 0; i < n; ++i) {
                 const int t = j * n + i;
                 const uint32_t ph = (uint32_t)t & 1u;
-                const float neg_lse2 = i == 0 ? lse_r[0] : i == 1 ? lse_r[1] : i == 2 ? lse_r[2] : lse_r[3];
-                const float nd = i == 0 ? dl_r[0] : i == 1 ? dl_r[1] : i == 2 ? dl_r[2] : dl_r[3];
+                const float neg_lse2 = -lse_nxt * LOG2E;
+                const float nd = -dl_nxt * p.scale;
+                {
+                    const int i2 = (i + 1 == n) ? 0 : i + 1;                     // query tile of the next pair (harmless reload after the last)
+                    lse_nxt = p.lse[bh * S + i2 * TQ + r];
+                    dl_nxt = p.delta[bh * S + i2 * TQ + r];
+                }
                 const unsigned long long drop_row = (unsigned long long)(bh * S + (i * TQ + r)) * (unsigned long long)S + j * TQ + kc;
                 uint32_t pk[16];                 // undropped P, packed bf16x2 (32 values)
                 uint32_t km[16];                 // keep-masks of my 32 columns (bf16x2 AND-masks)
@@ -780,6 +828,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
                 }
                 if (p.drop_on != 0u) attn_dropout_masks16(seed, p.drop_stream, drop_row >> 5, p.drop_k2, km);
                 TR(34, t);
+                if (i == 0 && j > 0) drain_kv(j - 1);
                 if (t >= 1) { mbar_wait(dv_done, ph ^ 1u); tc_fence_after(); }          // dV(t-1) retired: sP may be overwritten
                 TR(35, t);
                 // P~ = keep-mask AND P: the 1/(1-p) factor is folded into the dV drain and into the dS constants below
@@ -828,49 +877,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
                 if (lane == 0) mbar_arrive(ds_full);
                 TR(41, t);
             }
-            // ---- dV_j, dK_j complete: group 0 drains dK, group 1 drains dV (32 columns per warp).  The rows go through shared memory
-            // (P~ / dS staging is idle here: every MMA of the tile has retired) so that each global store instruction covers 4 rows x 128
-            // contiguous bytes: written straight from the row-per-lane registers, every STG.128 touched 32 different lines 6 KB apart
-            // and the 2048 line writes of one drain held the LSU for ~2000 clk -- the loads that open the next pair queued behind them
-            // (trace: ~2300-4300 idle clk at every kv-tile boundary).
-            mbar_wait(dkv_full, j & 1);
-            TR(42, j);
-            tc_fence_after();
-            {
-                uint32_t v[32];
-                tmem_ld32((g == 0 ? tmem_dK : tmem_dV) + lane_addr + c * 32, v);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(dkv_read);            // the accumulator columns are in registers: the next tile may overwrite them
-                if (g == 1 && p.drop_on != 0u) {                 // dV accumulated keep-mask AND P: apply the 1/(1-p) factor here
-#pragma unroll
-                    for (int k = 0; k < 32; ++k) v[k] = __float_as_uint(__uint_as_float(v[k]) * p.drop_scale);
-                }
-                const uint32_t stage = (g == 0) ? adS : aP;
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    st_shared_v4(stage + drain_off(r, 4 * c + k), pack_bf16(__uint_as_float(v[8 * k]), __uint_as_float(v[8 * k + 1])),
-                                 pack_bf16(__uint_as_float(v[8 * k + 2]), __uint_as_float(v[8 * k + 3])), pack_bf16(__uint_as_float(v[8 * k + 4]), __uint_as_float(v[8 * k + 5])),
-                                 pack_bf16(__uint_as_float(v[8 * k + 6]), __uint_as_float(v[8 * k + 7])));
-                if (p.dbias != nullptr) {                        // key / value bias gradients: column sums of the stored bf16 values
-                    float f[32];
-#pragma unroll
-                    for (int k = 0; k < 32; ++k) f[k] = __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[k])));
-                    dbias_acc += warp_column_sums32(f, lane);    // one atomic per head (below), not one per kv tile on the tile boundary
-                }
-                named_bar_sync(2 + g, BWD_GROUP_WARPS * 32);     // the group's 128 x 64 tile is staged
-                const int gw = c * 4 + q4;                       // warp index within the group: 16 rows each
-#pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                    const int row = gw * 16 + it * 4 + (lane >> 3), ch = lane & 7;
-                    const uint4 w = lds_u4(stage + drain_off(row, ch));
-                    const long long tok = (long long)b * p.tok_stride_b + (long long)(j * TQ + row) * p.tok_stride_s;
-                    st_global_v4(p.dqkv + tok * (3LL * p.H) + (g + 1) * p.H + h * HD + ch * 8, w.x, w.y, w.z, w.w);
-                }
-            }
-            named_bar_sync(1, BWD_COMPUTE_WARPS * 32);           // both staging tiles are read: P~ / dS of the next pair may be written
-            TR(43, j);
+            if (j + 1 == *s_nk_loop) drain_kv(j);              // the last tile has no following pair to hide behind
         }
         if (p.dbias != nullptr) atomicAdd(p.dbias + (g + 1) * p.H + h * HD + c * 32 + lane, dbias_acc);
         // ---- skipped (fully masked) kv tiles: zero dK / dV rows
