@@ -463,6 +463,8 @@ __device__ unsigned long long g_attn_cta[TRACE_MAX_CTAS][3];
 #define TR_END() do {} while (0)
 #endif
 
+// (608 threads leave 96 registers per thread, not 104: warps are placed 5 / 5 / 5 / 4 on the four 16 K-register sub-partitions, and a
+// __maxnreg__(104) build fails to launch)
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do, const AttnBwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
