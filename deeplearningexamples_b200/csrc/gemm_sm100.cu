@@ -13,6 +13,13 @@
 // (PyTorch/LanguageModeling/BERT/modeling.py:160,345-347,395,431,553) and fuses the reference's
 // separate pointwise passes (bias, tanh-GELU :121-122, dropout+residual :396-397/:432-433) into
 // the epilogue.
+// mbarrier waits of THIS kernel carry a suspend-time hint (the hardware parks the waiting warp instead of re-polling): the epilogue warps
+// wait ~2000 clk per tile for an accumulator, the producer waits on nearly every k-block for a free stage.  Same-box A/B on the whole step,
+// hint here only vs nowhere: GEMM launches 1211 -> 1224 TFLOP/s, 856.6 -> 859.3 seq/s (profiles/r02_gemm_mbar_hint_ab.log); the attention
+// kernels measure faster un-hinted (common.cuh) and keep the default.
+#ifndef DLE_MBAR_HINT_NS
+#define DLE_MBAR_HINT_NS 0x989680
+#endif
 #include "common.cuh"
 #include "../../include/dle_b200.h"
 
