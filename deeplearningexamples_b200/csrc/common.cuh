@@ -268,7 +268,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // launch fails with an error instead of hanging the GPU.
 // Suspend-time hint of mbarrier.try_wait: 0 = none (the hardware's default time limit per attempt), else nanoseconds.  Round 1 used
 // 10 ms to park single-lane waiters; since the producer / MMA warps wait warp-wide (see gemm_sm100.cu) the un-hinted form measures
-// 0.6 % faster on the whole step and 3 % on attention backward (profiles/README.md, same-box A/B), so it is the default.
+// 0.6 % faster on the whole step and 3 % on attention backward (profiles/README.md, same-box A/B), so it is the default; gemm_sm100.cu
+// defines the macro before including this header because the hinted form is the faster one for its long waits.
 #ifndef DLE_MBAR_HINT_NS
 #define DLE_MBAR_HINT_NS 0
 #endif
