@@ -565,6 +565,69 @@ class BertPreTrainedModel(nn.Module):
                 module.apex_enabled = val
         self.apply(_apply_flag)
 
+    # (old name, new name) substrings of checkpoints written before the reference renamed its modules (modeling.py:736-752)
+    _LEGACY_KEY_PARTS = (("gamma", "weight"), ("beta", "bias"), ("intermediate.dense.", "intermediate.dense_act."),
+                         ("pooler.dense.", "pooler.dense_act."))
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, state_dict=None, cache_dir=None, from_tf=False, distill_config=None,
+                        pooler=True, *inputs, **kwargs):
+        """Build the model from a local pretrained archive and load its weights: the fine-tuning entry of the reference
+        (modeling.py:655-786), same arguments and the same `(model, config)` return value.
+
+        `pretrained_model_name_or_path` is a directory (or a .tar.gz of one) holding `bert_config.json` and `pytorch_model.bin`;
+        `state_dict` replaces the weight file when given.  Checkpoint keys are mapped exactly as the reference does (LayerNorm
+        gamma/beta -> weight/bias, `intermediate.dense.` / `pooler.dense.` -> `..dense_act.`), a `bert.` prefix is dropped when this
+        class has no `bert` attribute (loading a pretraining checkpoint into `BertModel`), missing and unused keys are logged, shape
+        mismatches raise.  Not carried over: model names that resolve to downloads (no network: the reference logs an error and
+        returns None for an unknown name, and so does this), TensorFlow checkpoints (`from_tf`) and the distillation config
+        (out of scope) -- both raise NotImplementedError."""
+        import logging
+        import os
+        import shutil
+        import tarfile
+        import tempfile
+        log = logging.getLogger(__name__)
+        if from_tf:
+            raise NotImplementedError("TensorFlow checkpoints are not supported on this path (DESIGN.md section 7)")
+        if distill_config:
+            raise NotImplementedError("distillation is out of scope on this path (DESIGN.md section 7)")
+        path = str(pretrained_model_name_or_path)
+        if not os.path.exists(path):
+            log.error("Model name '%s' was not found: pretrained model names need a download and there is no network on this path; "
+                      "pass a directory or .tar.gz archive with bert_config.json and pytorch_model.bin", path)
+            return None
+        tmp = None
+        try:
+            if os.path.isdir(path):
+                root = path
+            else:
+                tmp = tempfile.mkdtemp(dir=cache_dir)
+                with tarfile.open(path, "r:gz") as tar:
+                    tar.extractall(tmp, filter="data")
+                root = tmp
+            config = BertConfig.from_json_file(os.path.join(root, "bert_config.json"))
+            model = cls(config, *inputs, **kwargs)
+            if state_dict is None:
+                state_dict = torch.load(os.path.join(root, "pytorch_model.bin"), map_location="cpu")
+        finally:
+            if tmp is not None:
+                shutil.rmtree(tmp, ignore_errors=True)
+        renamed = OrderedDict()
+        for key, value in state_dict.items():
+            for old, new in cls._LEGACY_KEY_PARTS:
+                if old in key:
+                    key = key.replace(old, new)          # (the rules are disjoint on real checkpoints; applied cumulatively)
+            renamed[key] = value
+        if not hasattr(model, "bert") and any(k.startswith("bert.") for k in renamed):
+            renamed = OrderedDict((k[len("bert."):], v) for k, v in renamed.items() if k.startswith("bert."))
+        result = model.load_state_dict(renamed, strict=False)    # raises RuntimeError on shape mismatches, like the reference
+        if result.missing_keys:
+            log.info("Weights of %s not initialized from pretrained model: %s", cls.__name__, result.missing_keys)
+        if result.unexpected_keys:
+            log.info("Weights from pretrained model not used in %s: %s", cls.__name__, result.unexpected_keys)
+        return model, config
+
 
 class BertModel(BertPreTrainedModel):
     """Embeddings + encoder + pooler (reference modeling.py:788-888).

@@ -57,3 +57,54 @@ def test_configs_match_reference_values():
     large = modeling.BertConfig.from_json_file(os.path.join(d, "large.json"))
     assert (large.hidden_size, large.num_hidden_layers, large.num_attention_heads, large.intermediate_size, large.vocab_size) == (1024, 24, 16, 4096, 30522)
     assert json.loads(large.to_json_string())["max_position_embeddings"] == 512
+
+
+def test_from_pretrained_maps_legacy_keys_and_prefixes(tmp_path):
+    """reference modeling.py:655-786: directory / .tar.gz archive with bert_config.json + pytorch_model.bin, legacy key names
+    (LayerNorm gamma/beta, intermediate.dense., pooler.dense.), `bert.` prefix dropped for the bare BertModel, (model, config) returned."""
+    import json
+    import tarfile
+    import torch
+    from deeplearningexamples_b200 import modeling as M
+    cfg = dict(vocab_size_or_config_json_file=96, hidden_size=64, num_hidden_layers=2, num_attention_heads=1, intermediate_size=128,
+               hidden_act="gelu", hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1, max_position_embeddings=32,
+               type_vocab_size=2, initializer_range=0.02)
+    torch.manual_seed(3)
+    src = M.BertForPreTraining(M.BertConfig(**cfg))
+    want = {k: v.clone() for k, v in src.state_dict().items()}
+
+    def legacy(k):                                   # what a checkpoint written by the older reference code calls this tensor
+        if "LayerNorm.weight" in k:
+            return k.replace("LayerNorm.weight", "LayerNorm.gamma")
+        if "LayerNorm.bias" in k:
+            return k.replace("LayerNorm.bias", "LayerNorm.beta")
+        return k.replace("intermediate.dense_act.", "intermediate.dense.").replace("pooler.dense_act.", "pooler.dense.")
+    old = {legacy(k): v for k, v in want.items()}
+    assert any("gamma" in k for k in old) and any("intermediate.dense." in k for k in old) and any("pooler.dense." in k for k in old)
+    d = tmp_path / "ckpt"
+    d.mkdir()
+    cfg_file = dict(cfg); cfg_file["vocab_size"] = cfg_file.pop("vocab_size_or_config_json_file")
+    (d / "bert_config.json").write_text(json.dumps(cfg_file))
+    torch.save(old, d / "pytorch_model.bin")
+
+    model, config = M.BertForPreTraining.from_pretrained(str(d))
+    assert isinstance(model, M.BertForPreTraining) and config.hidden_size == 64 and config.vocab_size == 96
+    got = model.state_dict()
+    assert set(got) == set(want)
+    for k in want:
+        assert torch.equal(got[k], want[k]), k
+
+    tar = tmp_path / "ckpt.tar.gz"                   # archive form
+    with tarfile.open(tar, "w:gz") as t:
+        t.add(d / "bert_config.json", arcname="bert_config.json")
+        t.add(d / "pytorch_model.bin", arcname="pytorch_model.bin")
+    bare, _ = M.BertModel.from_pretrained(str(tar))  # pretraining checkpoint into the bare encoder: `bert.` prefix dropped, heads unused
+    for k, v in bare.state_dict().items():
+        assert torch.equal(v, want["bert." + k]), k
+
+    qa, _ = M.BertForQuestionAnswering.from_pretrained(str(d), state_dict=dict(old))      # explicit state_dict; qa_outputs stays initialised
+    assert torch.equal(qa.state_dict()["bert.embeddings.word_embeddings.weight"], want["bert.embeddings.word_embeddings.weight"])
+    assert M.BertModel.from_pretrained("bert-large-uncased") is None                       # names need a download: error logged, None
+    bad = dict(old); bad["bert.embeddings.word_embeddings.weight"] = torch.zeros(5, 64)
+    with pytest.raises(RuntimeError):
+        M.BertForPreTraining.from_pretrained(str(d), state_dict=bad)
