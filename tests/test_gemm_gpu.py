@@ -95,6 +95,20 @@ def test_epilogue_dgelu_and_add():
     _close(out2, a.float() @ b.float() + u.float())
 
 
+@pytest.mark.parametrize("M,N,K", [(130, 264, 72), (1000, 776, 320), (4096, 4096, 1024)])
+def test_epilogue_dgelu_ragged_and_wide(M, N, K):
+    """The gelu'(u) epilogue runs on the 16-epilogue-warp instance of the kernel (four warps per TMEM lane quarter, 64 columns each, 3-stage
+    ring): partial row tiles, a last column tile with 8 valid columns, and the full FFN width, with the column sums."""
+    k, L = _k()
+    a, w, u = _rand((M, K), seed=50), _rand((K, N), 0.05, seed=51), _rand((M, N), 1.5, seed=52)
+    cs = torch.zeros(N, device="cuda")
+    out = k.gemm(a, w, b_layout=L.LAYOUT_MN, epilogue=L.EPI_DGELU, aux=u, colsum_out=cs)
+    uf = u.float().requires_grad_(True)
+    torch.nn.functional.gelu(uf, approximate="tanh").sum().backward()
+    _close(out, (a.float() @ w.float()) * uf.grad)
+    torch.testing.assert_close(cs, out.float().sum(dim=0), rtol=1e-3, atol=1e-2 * out.float().abs().sum(dim=0).max().item() + 1e-3)
+
+
 def test_epilogue_dropout_residual_statistics_and_determinism():
     k, L = _k()
     a, b, bias, res = _rand((1024, 256), seed=19), _rand((512, 256), 0.1, seed=20), _rand((512,), seed=21), _rand((1024, 512), seed=22)
